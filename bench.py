@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of geometric_adv on B200, one JSON line.
+
+Metric (BASELINE.json): Chamfer fwd+bwd point-pairs/s at N=2048.
+Workload (configs[1]): batched Chamfer forward+backward, B=50 clouds per rank,
+N=M=2048, U[-0.5,0.5) synthetic clouds, upstream gradients 1/2048 (what
+reduce_mean feeds, src/adv_ae.py:121).  A "step" = one nn_distance forward + one
+nn_distance_grad backward over the batch.  point-pairs per step = B*N*M per rank.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        our arm (CUDA, C ABI)
+  python bench.py --impl reference ...                       the reference's own CPU kernels
+
+Our arm: `value` is timed with CUDA events on the launching stream, inputs resident
+in HBM, L2 flushed between timed steps; `e2e` is the same step through the C ABI's
+host entry point (pinned HOST buffers in, HOST buffers out, copies inside the timed
+region).  `roofline` is for the dominant kernel (the forward NN search): algorithmic
+FLOPs = 8 per point pair against the FP32 FFMA peak measured by
+ga_probe_fp32_peak on the same device (MEASURED_PEAKS.json holds HBM / BF16 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, N, M = 50, 2048, 2048
+FLOP_PER_PAIR = 8.0
+METRIC = "chamfer_fwd_bwd_point_pairs_per_s_N2048"
+UNIT = "point-pairs/s"
+
+
+def make_inputs(rank):
+    rng1 = np.random.default_rng(2 + 1000 * rank)
+    rng2 = np.random.default_rng(3 + 1000 * rank)
+    a = (rng1.random((B, N, 3), dtype=np.float32) - np.float32(0.5)).astype(np.float32)
+    b = (rng2.random((B, M, 3), dtype=np.float32) - np.float32(0.5)).astype(np.float32)
+    gd1 = np.full((B, N), 1.0 / N, np.float32)
+    gd2 = np.full((B, M), 1.0 / M, np.float32)
+    return a, b, gd1, gd2
+
+
+def config(n_gpus):
+    return {
+        "workload": "configs[1]: batched Chamfer fwd+bwd, B=%d per GPU, N=M=%d (attack-batch shape)" % (B, N),
+        "batch_per_gpu": B, "n_points": N, "m_points": M, "global_batch": B * n_gpus,
+        "mode": "GA_MODE_CPU_EXACT (bit-identical to the reference CPU kernel)",
+        "cache": "L2 flushed between timed steps (256 MiB write)",
+        "sharding": "independent cloud pairs per rank, no data-path collective",
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_reference_pass(threads, a, b, gd1, gd2):
+    """One fwd+bwd pass of the reference's own CPU kernels (oracle/_ref, compiled unmodified),
+    or of the C port when the reference build did not travel.  Returns (seconds, kind)."""
+    from oracle import oracle as O
+    if O.have_ref():
+        t0 = time.perf_counter()
+        d1, i1, d2, i2 = O.ref_nn_distance(a, b, threads)
+        O.ref_nn_distance_grad(a, b, gd1, i1, gd2, i2, threads)
+        return time.perf_counter() - t0, "reference"
+    t0 = time.perf_counter()
+    d1, i1, d2, i2 = O.nn_distance(a, b, 0)
+    O.nn_distance_grad(a, b, gd1, i1, gd2, i2)
+    return time.perf_counter() - t0, "port"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    a, b, gd1, gd2 = make_inputs(0)
+    threads = host_threads() if O.have_ref() else 1
+    # bounded sample: SB clouds of the B=50 batch per step so a K-step run ends within minutes
+    sb = min(B, max(threads, 8))
+    aa, bb, g1, g2 = a[:sb], b[:sb], gd1[:sb], gd2[:sb]
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_pass(threads, aa, bb, g1, g2)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    kind = "port"
+    for _ in range(steps):
+        _, kind = cpu_reference_pass(threads, aa, bb, g1, g2)
+    dt = (time.perf_counter() - t0) / steps
+    value = sb * N * M / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (B / sb), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%d of the %d cloud pairs per step (fwd+bwd), %d steps; ms_per_step scaled to B=%d"
+                                   % (sb, B, steps, B)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    import geometric_adv_b200 as ga
+    from geometric_adv_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    a, b, gd1, gd2 = make_inputs(rank)
+    x1, x2 = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    g1, g2 = torch.from_numpy(gd1).to(dev), torch.from_numpy(gd2).to(dev)
+    d1 = torch.empty(B, N, device=dev)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
+    d2 = torch.empty(B, M, device=dev)
+    i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
+    o1 = torch.empty(B, N, 3, device=dev)
+    o2 = torch.empty(B, M, 3, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    p = ctypes.c_void_p
+
+    def fwd():
+        _lib.check(lib.ga_nn_distance_fwd(B, N, M, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()),
+                                          p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()), 0, p(stream)))
+
+    def bwd():
+        _lib.check(lib.ga_nn_distance_bwd(B, N, M, p(x1.data_ptr()), p(x2.data_ptr()), p(g1.data_ptr()),
+                                          p(i1.data_ptr()), p(g2.data_ptr()), p(i2.data_ptr()), p(o1.data_ptr()),
+                                          p(o2.data_ptr()), p(stream)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # FP32 roofline denominator, measured on this device
+    tf = ctypes.c_float()
+    ms = ctypes.c_float()
+    _lib.check(lib.ga_probe_fp32_peak(8192, ctypes.byref(tf), ctypes.byref(ms), p(stream)))
+    fp32_peak = float(tf.value)
+    lf = ctypes.c_float()
+    _lib.check(lib.ga_probe_launch_floor(200, ctypes.byref(lf), p(stream)))
+
+    for _ in range(max(3, args.warmup)):
+        flush.zero_()
+        fwd()
+        bwd()
+    barrier()
+
+    K = max(1, args.steps)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ga.launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for s in range(K):
+        flush.zero_()            # L2 flush, outside the event bracket
+        ev[s][0].record()
+        fwd()
+        ev[s][1].record()
+        bwd()
+        ev[s][2].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ga.launch_count() - launches0
+    # keep the sampler alive long enough to have seen load even for short runs
+    t_fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / K   # ms
+    t_bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    t_step = sum(e[0].elapsed_time(e[2]) for e in ev) / K
+
+    # sustained back-to-back loop (no flush) so the clock sampler sees load for >= 1 s
+    reps = max(200, int(1.0 / max(t_step * 1e-3, 1e-6)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fwd()
+        bwd()
+    e1.record()
+    torch.cuda.synchronize()
+    t_sustained = e0.elapsed_time(e1) / reps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: the C ABI host entry point, pinned host buffers in and out ----------------------
+    hx1, hx2 = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    hg1, hg2 = torch.from_numpy(gd1).pin_memory(), torch.from_numpy(gd2).pin_memory()
+    hd1 = torch.empty(B, N).pin_memory()
+    hi1 = torch.empty(B, N, dtype=torch.int32).pin_memory()
+    hd2 = torch.empty(B, M).pin_memory()
+    hi2 = torch.empty(B, M, dtype=torch.int32).pin_memory()
+    ho1 = torch.empty(B, N, 3).pin_memory()
+    ho2 = torch.empty(B, M, 3).pin_memory()
+
+    def e2e_step():
+        _lib.check(lib.ga_nn_distance_fwd_bwd_host(
+            B, N, M, p(hx1.data_ptr()), p(hx2.data_ptr()), p(hg1.data_ptr()), p(hg2.data_ptr()),
+            p(hd1.data_ptr()), p(hi1.data_ptr()), p(hd2.data_ptr()), p(hi2.data_ptr()), p(ho1.data_ptr()),
+            p(ho2.data_ptr()), 0))
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / K * 1e3  # ms, wall clock: the call returns with results on the host
+    h2d = (B * N * 3 + B * M * 3 + B * N + B * M) * 4
+    d2h = (2 * B * N + 2 * B * M + B * N * 3 + B * M * 3) * 4
+
+    # ---- max over ranks --------------------------------------------------------------------
+    times = torch.tensor([t_step, t_fwd, t_bwd, t_e2e, t_sustained], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_step, t_fwd, t_bwd, t_e2e, t_sustained = [float(x) for x in times.tolist()]
+
+    if rank == 0:
+        pairs = float(B) * N * M * world
+        per_gpu_pairs = float(B) * N * M
+        achieved = FLOP_PER_PAIR * per_gpu_pairs / (t_fwd * 1e-3) / 1e12
+        threads = host_threads()
+        from oracle import oracle as O
+        sb = min(B, max(threads, 8))
+        cpu_t, kind = cpu_reference_pass(threads if O.have_ref() else 1, a[:sb], b[:sb], gd1[:sb], gd2[:sb])
+        cpu1_t, _ = cpu_reference_pass(1, a[:4], b[:4], gd1[:4], gd2[:4])
+        line = {
+            "metric": METRIC, "value": pairs / (t_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(world),
+            "e2e": {"value": pairs / (t_e2e * 1e-3), "unit": UNIT, "ms_per_step": t_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "ga_nn_distance_fwd_bwd_host (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "kernel": "nn_fwd_kernel", "achieved": achieved, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                         "flop_per_point_pair": FLOP_PER_PAIR, "ms_per_launch": t_fwd,
+                         "peak_source": "ga_probe_fp32_peak (FFMA loop, measured on this device; "
+                                        "MEASURED_PEAKS.json has no FP32 entry)"},
+            "breakdown": {"fwd_ms": t_fwd, "bwd_ms": t_bwd, "sustained_ms_per_step_no_flush": t_sustained,
+                          "launch_floor_us": float(lf.value),
+                          "bwd_algorithmic_GBps": 32.0 * B * (N + M) / (t_bwd * 1e-3) / 1e9,
+                          "wall_s_timed_region": wall},
+            "cpu_baseline": {"value": sb * N * M / cpu_t, "unit": UNIT, "cores": threads if O.have_ref() else 1,
+                             "kind": kind,
+                             "sample": "%d of the %d cloud pairs, one fwd+bwd pass" % (sb, B),
+                             "single_thread_value": 4 * N * M / cpu1_t},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,189 @@
+// Library plumbing: error strings, launch counter, argument checks that repeat the
+// reference's OP_REQUIRES conditions and messages, and two measurement probes.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "ga_common.cuh"
+
+namespace ga {
+
+extern int g_fwd_variant;  // nn_distance_fwd.cu
+static thread_local char t_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), where);
+  return (int)e;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached = v;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+static int invalid(const char* msg) {
+  set_error("%s", msg);
+  return GA_ERR_INVALID_ARGUMENT;
+}
+
+static bool dims_eq2(int rank, const long long* d, long long a, long long b) {
+  return rank == 2 && d[0] == a && d[1] == b;
+}
+
+// ---- probes -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed) {
+  float a0 = seed + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f, c = 0.001f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456f) out[0] = s;  // never true; keeps the loop alive
+}
+
+__global__ void empty_kernel() {}
+
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" {
+
+int ga_version(void) { return 100; }
+
+int ga_set_tuning(int key, int value) {
+  if (key == 0) {
+    ga::g_fwd_variant = value;
+    return GA_OK;
+  }
+  ga::set_error("ga_set_tuning: unknown key %d", key);
+  return GA_ERR_INVALID_ARGUMENT;
+}
+const char* ga_last_error(void) { return t_err; }
+long long ga_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// tf_nndistance.cpp:51-58
+int ga_check_nn_distance(int rank1, const long long* dims1, int rank2, const long long* dims2) {
+  if (rank1 != 3) return invalid("NnDistance requires xyz1 be of shape (batch,#points,3)");
+  if (dims1[2] != 3) return invalid("NnDistance only accepts 3d point set xyz1");
+  if (rank2 != 3) return invalid("NnDistance requires xyz2 be of shape (batch,#points,3)");
+  if (dims2[2] != 3) return invalid("NnDistance only accepts 3d point set xyz2");
+  if (dims2[0] != dims1[0]) return invalid("NnDistance expects xyz1 and xyz2 have same batch size");
+  return GA_OK;
+}
+
+// tf_nndistance.cpp:91-104
+int ga_check_nn_distance_grad(int rank1, const long long* dims1, int rank2, const long long* dims2, int rank_gd1,
+                              const long long* dims_gd1, int rank_idx1, const long long* dims_idx1,
+                              int rank_gd2, const long long* dims_gd2, int rank_idx2,
+                              const long long* dims_idx2) {
+  if (rank1 != 3) return invalid("NnDistanceGrad requires xyz1 be of shape (batch,#points,3)");
+  if (dims1[2] != 3) return invalid("NnDistanceGrad only accepts 3d point set xyz1");
+  if (rank2 != 3) return invalid("NnDistanceGrad requires xyz2 be of shape (batch,#points,3)");
+  if (dims2[2] != 3) return invalid("NnDistanceGrad only accepts 3d point set xyz2");
+  if (dims2[0] != dims1[0]) return invalid("NnDistanceGrad expects xyz1 and xyz2 have same batch size");
+  const long long b = dims1[0], n = dims1[1], m = dims2[1];
+  if (rank_gd1 >= 0 && !dims_eq2(rank_gd1, dims_gd1, b, n))
+    return invalid("NnDistanceGrad requires grad_dist1 be of shape(batch,#points)");
+  if (rank_idx1 >= 0 && !dims_eq2(rank_idx1, dims_idx1, b, n))
+    return invalid("NnDistanceGrad requires idx1 be of shape(batch,#points)");
+  if (rank_gd2 >= 0 && !dims_eq2(rank_gd2, dims_gd2, b, m))
+    return invalid("NnDistanceGrad requires grad_dist2 be of shape(batch,#points)");
+  if (rank_idx2 >= 0 && !dims_eq2(rank_idx2, dims_idx2, b, m))
+    return invalid("NnDistanceGrad requires idx2 be of shape(batch,#points)");
+  return GA_OK;
+}
+
+// tf_grouping.cpp:112-113,118
+int ga_check_selection_sort(int k, int rank, const long long* dims) {
+  (void)dims;
+  if (!(k > 0)) return invalid("SelectionSort expects positive k");
+  if (rank != 3) return invalid("SelectionSort expects (b,m,n) dist shape.");
+  return GA_OK;
+}
+
+// tf_grouping.cpp:149,155
+int ga_check_group_point(int rank_points, const long long* dims_points, int rank_idx, const long long* dims_idx) {
+  if (rank_points != 3) return invalid("GroupPoint expects (batch_size, num_points, channel) points shape");
+  if (!(rank_idx == 3 && dims_idx[0] == dims_points[0]))
+    return invalid("GroupPoint expects (batch_size, npoints, nsample) idx shape");
+  return GA_OK;
+}
+
+int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  if (iters <= 0) iters = 4096;
+  const int blocks = sm_count() * 8, threads = 256;
+  float* sink = nullptr;
+  GA_CUDA_TRY(cudaMalloc(&sink, sizeof(float)));
+  cudaEvent_t e0, e1;
+  GA_CUDA_TRY(cudaEventCreate(&e0));
+  GA_CUDA_TRY(cudaEventCreate(&e1));
+  fp32_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 1.0f);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    GA_CUDA_TRY(cudaEventRecord(e0, st));
+    fp32_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 1.0f);
+    GA_CUDA_TRY(cudaEventRecord(e1, st));
+    GA_CUDA_TRY(cudaEventSynchronize(e1));
+    float t = 0;
+    GA_CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+    if (t < best) best = t;
+    count_launch();
+  }
+  GA_LAUNCH_CHECK("fp32_peak_kernel");
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  const double flop = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+  if (tflops) *tflops = (float)(flop / (best * 1e-3) / 1e12);
+  if (ms) *ms = best;
+  return GA_OK;
+}
+
+int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  if (reps <= 0) reps = 200;
+  cudaEvent_t e0, e1;
+  GA_CUDA_TRY(cudaEventCreate(&e0));
+  GA_CUDA_TRY(cudaEventCreate(&e1));
+  for (int i = 0; i < 10; i++) empty_kernel<<<1, 32, 0, st>>>();
+  GA_CUDA_TRY(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps; i++) empty_kernel<<<1, 32, 0, st>>>();
+  GA_CUDA_TRY(cudaEventRecord(e1, st));
+  GA_CUDA_TRY(cudaEventSynchronize(e1));
+  float t = 0;
+  GA_CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+  GA_LAUNCH_CHECK("empty_kernel");
+  count_launch(reps + 9);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (us) *us = t * 1000.0f / reps;
+  return GA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+// HOST-pointer entry points: the drop-in for the reference's CPU-tensor kernels
+// (REGISTER_KERNEL_BUILDER(... DEVICE_CPU ...), tf_nndistance.cpp:83,166).  The
+// caller's buffers are copied to a per-thread device arena, the device entry
+// points run on a per-thread stream, results are copied straight back into the
+// caller's memory.  Pinned caller memory gives true async DMA; pageable memory
+// works too (the driver stages it).
+#include "ga_common.cuh"
+
+namespace ga {
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  // deliberately no destructor: at process teardown the CUDA context may already be gone
+};
+static thread_local Arena t_arena;
+
+static int arena_reserve(size_t bytes, char** base, cudaStream_t* st) {
+  int dev = 0;
+  GA_CUDA_TRY(cudaGetDevice(&dev));
+  Arena& A = t_arena;
+  if (A.dev != dev) {
+    if (A.base) cudaFree(A.base);
+    if (A.stream) cudaStreamDestroy(A.stream);
+    A.base = nullptr;
+    A.cap = 0;
+    A.stream = nullptr;
+    A.dev = dev;
+  }
+  if (!A.stream) GA_CUDA_TRY(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
+  if (bytes > A.cap) {
+    if (A.base) {
+      GA_CUDA_TRY(cudaStreamSynchronize(A.stream));
+      GA_CUDA_TRY(cudaFree(A.base));
+      A.base = nullptr;
+      A.cap = 0;
+    }
+    size_t want = bytes + (bytes >> 2) + (1u << 20);
+    GA_CUDA_TRY(cudaMalloc(&A.base, want));
+    A.cap = want;
+  }
+  *base = A.base;
+  *st = A.stream;
+  return GA_OK;
+}
+
+struct Carver {
+  char* p;
+  size_t off = 0;
+  explicit Carver(char* base) : p(base) {}
+  template <class T>
+  T* take(size_t count) {
+    T* r = reinterpret_cast<T*>(p + off);
+    off += (count * sizeof(T) + 255) & ~(size_t)255;
+    return r;
+  }
+};
+static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+#define GA_TRY(expr)             \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != GA_OK) return _rc; \
+  } while (0)
+
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" {
+
+int ga_nn_distance_fwd_host(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1, int* idx1,
+                            float* dist2, int* idx2, int mode) {
+  if (b < 0 || n < 0 || m < 0) {
+    set_error("ga_nn_distance_fwd_host: negative size");
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  const size_t e1 = (size_t)b * n, e2 = (size_t)b * m;
+  if (e1 + e2 == 0) return GA_OK;
+  char* base;
+  cudaStream_t st;
+  GA_TRY(arena_reserve(padded(e1 * 12) + padded(e2 * 12) + 2 * padded(e1 * 4) + 2 * padded(e2 * 4), &base, &st));
+  Carver c(base);
+  float* d_x1 = c.take<float>(e1 * 3);
+  float* d_x2 = c.take<float>(e2 * 3);
+  float* d_d1 = c.take<float>(e1);
+  int* d_i1 = c.take<int>(e1);
+  float* d_d2 = c.take<float>(e2);
+  int* d_i2 = c.take<int>(e2);
+  if (e1) GA_CUDA_TRY(cudaMemcpyAsync(d_x1, xyz1, e1 * 12, cudaMemcpyHostToDevice, st));
+  if (e2) GA_CUDA_TRY(cudaMemcpyAsync(d_x2, xyz2, e2 * 12, cudaMemcpyHostToDevice, st));
+  GA_TRY(ga_nn_distance_fwd(b, n, m, d_x1, d_x2, d_d1, d_i1, d_d2, d_i2, mode, (ga_stream_t)st));
+  if (e1) {
+    GA_CUDA_TRY(cudaMemcpyAsync(dist1, d_d1, e1 * 4, cudaMemcpyDeviceToHost, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(idx1, d_i1, e1 * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (e2) {
+    GA_CUDA_TRY(cudaMemcpyAsync(dist2, d_d2, e2 * 4, cudaMemcpyDeviceToHost, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(idx2, d_i2, e2 * 4, cudaMemcpyDeviceToHost, st));
+  }
+  GA_CUDA_TRY(cudaStreamSynchronize(st));
+  return GA_OK;
+}
+
+int ga_nn_distance_bwd_host(int b, int n, int m, const float* xyz1, const float* xyz2, const float* grad_dist1,
+                            const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1,
+                            float* grad_xyz2) {
+  if (b < 0 || n < 0 || m < 0) {
+    set_error("ga_nn_distance_bwd_host: negative size");
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  const size_t e1 = (size_t)b * n, e2 = (size_t)b * m;
+  if (e1 + e2 == 0) return GA_OK;
+  char* base;
+  cudaStream_t st;
+  GA_TRY(arena_reserve(2 * padded(e1 * 12) + 2 * padded(e2 * 12) + 2 * padded(e1 * 4) + 2 * padded(e2 * 4), &base,
+                       &st));
+  Carver c(base);
+  float* d_x1 = c.take<float>(e1 * 3);
+  float* d_x2 = c.take<float>(e2 * 3);
+  float* d_g1 = c.take<float>(e1);
+  int* d_i1 = c.take<int>(e1);
+  float* d_g2 = c.take<float>(e2);
+  int* d_i2 = c.take<int>(e2);
+  float* d_o1 = c.take<float>(e1 * 3);
+  float* d_o2 = c.take<float>(e2 * 3);
+  if (e1) {
+    GA_CUDA_TRY(cudaMemcpyAsync(d_x1, xyz1, e1 * 12, cudaMemcpyHostToDevice, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(d_g1, grad_dist1, e1 * 4, cudaMemcpyHostToDevice, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(d_i1, idx1, e1 * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (e2) {
+    GA_CUDA_TRY(cudaMemcpyAsync(d_x2, xyz2, e2 * 12, cudaMemcpyHostToDevice, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(d_g2, grad_dist2, e2 * 4, cudaMemcpyHostToDevice, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(d_i2, idx2, e2 * 4, cudaMemcpyHostToDevice, st));
+  }
+  GA_TRY(ga_nn_distance_bwd(b, n, m, d_x1, d_x2, d_g1, d_i1, d_g2, d_i2, d_o1, d_o2, (ga_stream_t)st));
+  if (e1) GA_CUDA_TRY(cudaMemcpyAsync(grad_xyz1, d_o1, e1 * 12, cudaMemcpyDeviceToHost, st));
+  if (e2) GA_CUDA_TRY(cudaMemcpyAsync(grad_xyz2, d_o2, e2 * 12, cudaMemcpyDeviceToHost, st));
+  GA_CUDA_TRY(cudaStreamSynchronize(st));
+  return GA_OK;
+}
+
+int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const float* xyz2,
+                                const float* grad_dist1, const float* grad_dist2, float* dist1, int* idx1,
+                                float* dist2, int* idx2, float* grad_xyz1, float* grad_xyz2, int mode) {
+  if (b < 0 || n < 0 || m < 0) {
+    set_error("ga_nn_distance_fwd_bwd_host: negative size");
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  const size_t e1 = (size_t)b * n, e2 = (size_t)b * m;
+  if (e1 + e2 == 0) return GA_OK;
+  char* base;
+  cudaStream_t st;
+  GA_TRY(arena_reserve(2 * padded(e1 * 12) + 2 * padded(e2 * 12) + 3 * padded(e1 * 4) + 3 * padded(e2 * 4), &base,
+                       &st));
+  Carver c(base);
+  float* d_x1 = c.take<float>(e1 * 3);
+  float* d_x2 = c.take<float>(e2 * 3);
+  float* d_g1 = c.take<float>(e1);
+  float* d_g2 = c.take<float>(e2);
+  float* d_d1 = c.take<float>(e1);
+  int* d_i1 = c.take<int>(e1);
+  float* d_d2 = c.take<float>(e2);
+  int* d_i2 = c.take<int>(e2);
+  float* d_o1 = c.take<float>(e1 * 3);
+  float* d_o2 = c.take<float>(e2 * 3);
+  if (e1) {
+    GA_CUDA_TRY(cudaMemcpyAsync(d_x1, xyz1, e1 * 12, cudaMemcpyHostToDevice, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(d_g1, grad_dist1, e1 * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (e2) {
+    GA_CUDA_TRY(cudaMemcpyAsync(d_x2, xyz2, e2 * 12, cudaMemcpyHostToDevice, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(d_g2, grad_dist2, e2 * 4, cudaMemcpyHostToDevice, st));
+  }
+  GA_TRY(ga_nn_distance_fwd(b, n, m, d_x1, d_x2, d_d1, d_i1, d_d2, d_i2, mode, (ga_stream_t)st));
+  GA_TRY(ga_nn_distance_bwd(b, n, m, d_x1, d_x2, d_g1, d_i1, d_g2, d_i2, d_o1, d_o2, (ga_stream_t)st));
+  if (e1) {
+    GA_CUDA_TRY(cudaMemcpyAsync(dist1, d_d1, e1 * 4, cudaMemcpyDeviceToHost, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(idx1, d_i1, e1 * 4, cudaMemcpyDeviceToHost, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(grad_xyz1, d_o1, e1 * 12, cudaMemcpyDeviceToHost, st));
+  }
+  if (e2) {
+    GA_CUDA_TRY(cudaMemcpyAsync(dist2, d_d2, e2 * 4, cudaMemcpyDeviceToHost, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(idx2, d_i2, e2 * 4, cudaMemcpyDeviceToHost, st));
+    GA_CUDA_TRY(cudaMemcpyAsync(grad_xyz2, d_o2, e2 * 12, cudaMemcpyDeviceToHost, st));
+  }
+  GA_CUDA_TRY(cudaStreamSynchronize(st));
+  return GA_OK;
+}
+
+int ga_knn_host(int b, int n, int m, int k, const float* xyz1, const float* xyz2, float* val, int* idx) {
+  if (b < 0 || n < 0 || m < 0 || k <= 0) {
+    set_error(k <= 0 ? "SelectionSort expects positive k" : "ga_knn_host: negative size");
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  const size_t e1 = (size_t)b * n, e2 = (size_t)b * m, eo = (size_t)b * m * k;
+  if (e2 == 0) return GA_OK;
+  char* base;
+  cudaStream_t st;
+  GA_TRY(arena_reserve(padded(e1 * 12) + padded(e2 * 12) + 2 * padded(eo * 4), &base, &st));
+  Carver c(base);
+  float* d_x1 = c.take<float>(e1 * 3);
+  float* d_x2 = c.take<float>(e2 * 3);
+  float* d_v = c.take<float>(eo);
+  int* d_i = c.take<int>(eo);
+  if (e1) GA_CUDA_TRY(cudaMemcpyAsync(d_x1, xyz1, e1 * 12, cudaMemcpyHostToDevice, st));
+  GA_CUDA_TRY(cudaMemcpyAsync(d_x2, xyz2, e2 * 12, cudaMemcpyHostToDevice, st));
+  GA_TRY(ga_knn(b, n, m, k, d_x1, d_x2, d_v, d_i, (ga_stream_t)st));
+  GA_CUDA_TRY(cudaMemcpyAsync(val, d_v, eo * 4, cudaMemcpyDeviceToHost, st));
+  GA_CUDA_TRY(cudaMemcpyAsync(idx, d_i, eo * 4, cudaMemcpyDeviceToHost, st));
+  GA_CUDA_TRY(cudaStreamSynchronize(st));
+  return GA_OK;
+}
+
+int ga_knn_dists_host(int b, int n, int k, const float* pc, float* out) {
+  if (b < 0 || n < 0 || k <= 0) {
+    set_error(k <= 0 ? "SelectionSort expects positive k" : "ga_knn_dists_host: negative size");
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  const size_t e1 = (size_t)b * n, eo = (size_t)b * n * k;
+  if (e1 == 0) return GA_OK;
+  char* base;
+  cudaStream_t st;
+  GA_TRY(arena_reserve(padded(e1 * 12) + padded(eo * 4), &base, &st));
+  Carver c(base);
+  float* d_x = c.take<float>(e1 * 3);
+  float* d_o = c.take<float>(eo);
+  GA_CUDA_TRY(cudaMemcpyAsync(d_x, pc, e1 * 12, cudaMemcpyHostToDevice, st));
+  GA_TRY(ga_knn_dists(b, n, k, d_x, d_o, (ga_stream_t)st));
+  GA_CUDA_TRY(cudaMemcpyAsync(out, d_o, eo * 4, cudaMemcpyDeviceToHost, st));
+  GA_CUDA_TRY(cudaStreamSynchronize(st));
+  return GA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// Chamfer backward: gradient of nn_distance w.r.t. both clouds, atomic-free.
+// Replaces NmDistanceGradKernel x2 + 2 memsets (tf_nndistance_g.cu:132-157,
+// chamfer3D.cu:155-195) and reproduces NnDistanceGradOp's CPU loops
+// (tf_nndistance.cpp:122-163) bit for bit.
+//
+// The reference scatters with atomicAdd (order-nondeterministic).  The CPU loops
+// fix a summation order per output element:
+//   grad_xyz1[j]: 0 + g1[j]*(x1[j]-x2[idx1[j]])            (loop 1, direct)
+//                 then -= g2[j']*(x2[j']-x1[j]) for every j' with idx2[j']==j,
+//                 ascending j'                                  (loop 2, scatter)
+//   grad_xyz2[k]: 0, then -= g1[j]*(x1[j]-x2[k]) for every j with idx1[j]==k,
+//                 ascending j (loop 1, scatter), then += g2[k]*(x2[k]-x1[idx2[k]]).
+// One CTA per (batch element, output cloud) inverts the index map with a STABLE
+// counting sort in shared memory (per-warp count tables + match.any ranks), then
+// one thread per output point walks its contributor list in ascending order with
+// unfused __fmul_rn/__fadd_rn.  Every output element is written exactly once, so
+// no memset is needed and the result is run-to-run reproducible.
+#include "ga_common.cuh"
+
+namespace ga {
+
+constexpr int kBwdThreads = 512;
+constexpr int kBwdWarps = kBwdThreads / 32;
+constexpr int kBwdKeys = 2048;  // keys (output points) handled per pass
+
+struct BwdArgs {
+  int b, n, m;
+  const float* xyz1;
+  const float* xyz2;
+  const float* gd1;
+  const int* idx1;
+  const float* gd2;
+  const int* idx2;
+  float* gxyz1;
+  float* gxyz2;
+};
+
+// smem: cnt[W][K] u16 | total[K] i32 | start[K] i32 | wsum[W] i32 | order[L] u16
+static size_t bwd_smem_bytes(int lmax) {
+  return (size_t)kBwdWarps * kBwdKeys * 2 + (size_t)kBwdKeys * 4 * 2 + 64 * 4 + (((size_t)lmax * 2 + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
+  constexpr int W = kBwdWarps, K = kBwdKeys;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned short* cnt = reinterpret_cast<unsigned short*>(smem_raw);            // [W][K]
+  int* total = reinterpret_cast<int*>(smem_raw + (size_t)W * K * 2);           // [K]
+  int* start = total + K;                                                      // [K]
+  int* wsum = start + K;                                                       // [64]
+  unsigned short* order = reinterpret_cast<unsigned short*>(wsum + 64);        // [L]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int batch = blockIdx.x >> 1;
+  const int side = blockIdx.x & 1;
+  // own = the cloud whose gradient this CTA produces (P points); oth = the other (L points)
+  const int P = side ? a.m : a.n;
+  const int L = side ? a.n : a.m;
+  const float* own = (side ? a.xyz2 : a.xyz1) + (size_t)batch * P * 3;
+  const float* oth = (side ? a.xyz1 : a.xyz2) + (size_t)batch * L * 3;
+  const float* own_gd = (side ? a.gd2 : a.gd1) + (size_t)batch * P;
+  const int* own_idx = (side ? a.idx2 : a.idx1) + (size_t)batch * P;
+  const float* oth_gd = (side ? a.gd1 : a.gd2) + (size_t)batch * L;
+  const int* oth_idx = (side ? a.idx1 : a.idx2) + (size_t)batch * L;
+  float* out = (side ? a.gxyz2 : a.gxyz1) + (size_t)batch * P * 3;
+
+  const int seg = ((L + W - 1) / W + 31) & ~31;  // elements per warp, multiple of 32
+  const int e_begin = warp * seg;
+  const int e_end = min(L, e_begin + seg);
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int k0 = 0; k0 < P; k0 += K) {
+    const int kn = min(K, P - k0);
+    // 1. zero the per-warp count tables
+    {
+      uint32_t* z = reinterpret_cast<uint32_t*>(cnt);
+      for (int i = tid; i < W * K / 2; i += kBwdThreads) z[i] = 0u;
+    }
+    __syncthreads();
+    // 2. per-warp histogram of its contiguous element segment
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+      const int e = e0 + lane;
+      int key = -1 - lane;
+      if (e < e_end) {
+        const int kk = __ldg(oth_idx + e) - k0;
+        if (kk >= 0 && kk < kn) key = kk;
+      }
+      const unsigned mask = __match_any_sync(0xffffffffu, key);
+      if (key >= 0 && (mask & lt_mask) == 0u) cnt[warp * K + key] += (unsigned short)__popc(mask);
+      __syncwarp();
+    }
+    __syncthreads();
+    // 3. exclusive prefix over warps per key; per-key totals
+    for (int k = tid; k < K; k += kBwdThreads) {
+      int run = 0;
+#pragma unroll
+      for (int w = 0; w < W; w++) {
+        const int c = cnt[w * K + k];
+        cnt[w * K + k] = (unsigned short)run;
+        run += c;
+      }
+      total[k] = run;
+    }
+    __syncthreads();
+    // 4. exclusive scan of totals over keys (K = 4 keys per thread at 512 threads)
+    {
+      constexpr int PER = K / kBwdThreads;
+      int loc[PER];
+      int s = 0;
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        loc[i] = s;
+        s += total[tid * PER + i];
+      }
+      int incl = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      int woff = 0;
+      for (int w = 0; w < warp; w++) woff += wsum[w];
+      const int base = woff + incl - s;
+#pragma unroll
+      for (int i = 0; i < PER; i++) start[tid * PER + i] = base + loc[i];
+    }
+    __syncthreads();
+    // 5. stable placement: same walk as step 2, ranks within a warp chunk from match.any
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+      const int e = e0 + lane;
+      int key = -1 - lane;
+      if (e < e_end) {
+        const int kk = __ldg(oth_idx + e) - k0;
+        if (kk >= 0 && kk < kn) key = kk;
+      }
+      const unsigned mask = __match_any_sync(0xffffffffu, key);
+      if (key >= 0) {
+        const int r = __popc(mask & lt_mask);
+        const int off = cnt[warp * K + key];
+        order[start[key] + off + r] = (unsigned short)e;
+      }
+      __syncwarp();
+      if (key >= 0 && (mask & lt_mask) == 0u) cnt[warp * K + key] += (unsigned short)__popc(mask);
+      __syncwarp();
+    }
+    __syncthreads();
+    // 6. one thread per output point, contributors in ascending order
+    for (int k = tid; k < kn; k += kBwdThreads) {
+      const int p = k0 + k;
+      const float ox = __ldg(own + (size_t)p * 3), oy = __ldg(own + (size_t)p * 3 + 1),
+                  oz = __ldg(own + (size_t)p * 3 + 2);
+      // direct term (own loop of the reference)
+      float dx = 0.f, dy = 0.f, dz = 0.f;
+      {
+        const int j2 = __ldg(own_idx + p);
+        if (j2 >= 0 && j2 < L) {
+          const float g = __fmul_rn(__ldg(own_gd + p), 2.0f);
+          dx = __fmul_rn(g, __fsub_rn(ox, __ldg(oth + (size_t)j2 * 3)));
+          dy = __fmul_rn(g, __fsub_rn(oy, __ldg(oth + (size_t)j2 * 3 + 1)));
+          dz = __fmul_rn(g, __fsub_rn(oz, __ldg(oth + (size_t)j2 * 3 + 2)));
+        }
+      }
+      float ax = 0.f, ay = 0.f, az = 0.f;
+      if (side == 0) {  // loop 1 (direct) runs before loop 2 (scatter) for cloud 1
+        ax = __fadd_rn(ax, dx);
+        ay = __fadd_rn(ay, dy);
+        az = __fadd_rn(az, dz);
+      }
+      const int s0 = start[k], s1 = s0 + total[k];
+      for (int s = s0; s < s1; s++) {
+        const int e = order[s];
+        const float g = __fmul_rn(__ldg(oth_gd + e), 2.0f);
+        const float tx = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3), ox));
+        const float ty = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 1), oy));
+        const float tz = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 2), oz));
+        ax = __fsub_rn(ax, tx);
+        ay = __fsub_rn(ay, ty);
+        az = __fsub_rn(az, tz);
+      }
+      if (side == 1) {  // for cloud 2 the scatter of loop 1 comes first, its own loop 2 last
+        ax = __fadd_rn(ax, dx);
+        ay = __fadd_rn(ay, dy);
+        az = __fadd_rn(az, dz);
+      }
+      out[(size_t)p * 3] = ax;
+      out[(size_t)p * 3 + 1] = ay;
+      out[(size_t)p * 3 + 2] = az;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace ga
+
+extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const float* xyz2,
+                                  const float* grad_dist1, const int* idx1, const float* grad_dist2,
+                                  const int* idx2, float* grad_xyz1, float* grad_xyz2, ga_stream_t stream) {
+  using namespace ga;
+  if (b < 0 || n < 0 || m < 0) {
+    set_error("ga_nn_distance_bwd: negative size (b=%d n=%d m=%d)", b, n, m);
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  if (b == 0 || (n == 0 && m == 0)) return GA_OK;
+  cudaStream_t st = as_stream(stream);
+  // A cloud whose partner is empty only ever sees idx = 0 into nothing: the reference
+  // would read out of bounds.  We define the gradient as zero there.
+  if (n == 0 || m == 0) {
+    if (n > 0) GA_CUDA_TRY(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3, st));
+    if (m > 0) GA_CUDA_TRY(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3, st));
+    return GA_OK;
+  }
+  const int lmax = n > m ? n : m;
+  if (lmax > 65536) {
+    set_error("ga_nn_distance_bwd: clouds larger than 65536 points are not supported (n=%d m=%d)", n, m);
+    return GA_ERR_UNSUPPORTED;
+  }
+  if ((long long)b * 2 > 0x7fffffffLL) {
+    set_error("ga_nn_distance_bwd: batch too large");
+    return GA_ERR_UNSUPPORTED;
+  }
+  const size_t smem = bwd_smem_bytes(lmax);
+  GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BwdArgs a;
+  a.b = b; a.n = n; a.m = m;
+  a.xyz1 = xyz1; a.xyz2 = xyz2;
+  a.gd1 = grad_dist1; a.idx1 = idx1; a.gd2 = grad_dist2; a.idx2 = idx2;
+  a.gxyz1 = grad_xyz1; a.gxyz2 = grad_xyz2;
+  nn_bwd_kernel<<<(unsigned)(2 * b), kBwdThreads, smem, st>>>(a);
+  GA_LAUNCH_CHECK("nn_bwd_kernel");
+  return GA_OK;
+}

@@ -1,0 +1,51 @@
+// Small epilogue kernels around the Chamfer outputs.
+#include "ga_common.cuh"
+
+namespace ga {
+
+// out[i] = mean(dist1[i,:]) + mean(dist2[i,:])  (src/adv_ae.py:120-121,
+// attacker/prepare_indices_for_attack.py:113-114).  Fixed order: each thread sums a
+// strided slice in ascending order, then a fixed shuffle/smem tree.
+__global__ void __launch_bounds__(256) chamfer_per_cloud_kernel(int n, int m, const float* __restrict__ dist1,
+                                                               const float* __restrict__ dist2,
+                                                               float* __restrict__ out) {
+  __shared__ float part[2][8];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = tid; j < n; j += 256) s1 += dist1[(size_t)i * n + j];
+  for (int j = tid; j < m; j += 256) s2 += dist2[(size_t)i * m + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((tid & 31) == 0) {
+    part[0][tid >> 5] = s1;
+    part[1][tid >> 5] = s2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      a += part[0][w];
+      b += part[1][w];
+    }
+    out[i] = a / (float)n + b / (float)m;
+  }
+}
+
+}  // namespace ga
+
+extern "C" int ga_chamfer_per_cloud(int b, int n, int m, const float* dist1, const float* dist2, float* out,
+                                    ga_stream_t stream) {
+  using namespace ga;
+  if (b < 0 || n < 0 || m < 0) {
+    set_error("ga_chamfer_per_cloud: negative size");
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  if (b == 0) return GA_OK;
+  chamfer_per_cloud_kernel<<<b, 256, 0, as_stream(stream)>>>(n, m, dist1, dist2, out);
+  GA_LAUNCH_CHECK("chamfer_per_cloud_kernel");
+  return GA_OK;
+}

@@ -1,0 +1,344 @@
+"""PyTorch shim over libga_b200.so that keeps the reference's operator signatures.
+
+Reference interfaces mirrored here (paths below the reference tree):
+
+* ``nn_distance(xyz1, xyz2) -> dist1, idx1, dist2, idx2``
+  external/structural_losses/tf_nndistance.py:15-26, gradient :35-41
+* ``nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2)``
+  the NnDistanceGrad op, tf_nndistance.cpp:10-18
+* ``chamfer_3DDist()(a, b) -> dist1, dist2, idx1, idx2``
+  transfer/atlasnet/auxiliary/ChamferDistancePytorch/chamfer3D/dist_chamfer_3D.py:26-74
+* ``knn_point(k, xyz1, xyz2) -> val, idx``       external/grouping/tf_grouping.py:48-75
+* ``select_top_k(k, dist) -> idx, dist_out``      tf_grouping.py:22-31
+* ``group_point(points, idx)``                    tf_grouping.py:33-47
+
+CUDA tensors run on the caller's current stream (CUDA-graph capturable); CPU
+tensors go through the library's ``*_host`` entry points, which stage through the
+GPU -- the same kernels, not a CPU implementation.  torch supplies memory and
+streams only; all arithmetic happens in the library.
+"""
+import torch
+
+from . import _lib
+from ._lib import GA_MODE_CPU_EXACT, GA_MODE_GPU_REF
+
+__all__ = [
+    "nn_distance", "nn_distance_grad", "chamfer_3DDist", "chamfer_3DFunction", "knn_point", "select_top_k",
+    "group_point", "knn_dists", "chamfer_per_cloud", "chamfer_all_pairs", "set_default_mode", "launch_count",
+    "GA_MODE_CPU_EXACT", "GA_MODE_GPU_REF",
+]
+
+_default_mode = GA_MODE_CPU_EXACT
+
+
+def set_default_mode(mode):
+    """GA_MODE_CPU_EXACT (bit-identical to the reference CPU kernel, default) or
+    GA_MODE_GPU_REF (bit-identical to the reference CUDA kernel's FMA contraction)."""
+    global _default_mode
+    if mode not in (GA_MODE_CPU_EXACT, GA_MODE_GPU_REF):
+        raise ValueError("unknown mode %r" % (mode,))
+    _default_mode = mode
+
+
+def launch_count():
+    return int(_lib.load().ga_launch_count())
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _prep(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if t.dtype != dtype:
+        # the reference ops are registered for float32 / int32 only (tf_nndistance.cpp:4-9)
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()  # dist_chamfer_3D.py:72-73 does the same
+
+
+def _same_device(*ts):
+    d = ts[0].device
+    for t in ts[1:]:
+        if t.device != d:
+            raise ValueError("all tensors must live on the same device (%s vs %s)" % (d, t.device))
+    return d
+
+
+class _Guard:
+    """Make the tensor's device current for the duration of a launch."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.prev = None
+
+    def __enter__(self):
+        if self.dev.type == "cuda" and torch.cuda.current_device() != self.dev.index:
+            self.prev = torch.cuda.current_device()
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+# --------------------------------------------------------------------------- nn_distance
+def _nn_distance_fwd(xyz1, xyz2, mode):
+    lib = _lib.load()
+    _lib.check(lib.ga_check_nn_distance(xyz1.dim(), _lib.dims(xyz1.shape), xyz2.dim(), _lib.dims(xyz2.shape)))
+    xyz1 = _prep(xyz1, torch.float32, "xyz1")
+    xyz2 = _prep(xyz2, torch.float32, "xyz2")
+    dev = _same_device(xyz1, xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+    idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+    dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+    idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+    if dev.type == "cuda":
+        with _Guard(dev):
+            rc = lib.ga_nn_distance_fwd(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(),
+                                        idx1.data_ptr(), dist2.data_ptr(), idx2.data_ptr(), mode, _stream(xyz1))
+    else:
+        rc = lib.ga_nn_distance_fwd_host(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(),
+                                         idx1.data_ptr(), dist2.data_ptr(), idx2.data_ptr(), mode)
+    _lib.check(rc)
+    return dist1, idx1, dist2, idx2
+
+
+def nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
+    """NnDistanceGrad (tf_nndistance.cpp:84-166): returns grad_xyz1 (b,n,3), grad_xyz2 (b,m,3)."""
+    lib = _lib.load()
+    _lib.check(lib.ga_check_nn_distance_grad(
+        xyz1.dim(), _lib.dims(xyz1.shape), xyz2.dim(), _lib.dims(xyz2.shape),
+        grad_dist1.dim(), _lib.dims(grad_dist1.shape), idx1.dim(), _lib.dims(idx1.shape),
+        grad_dist2.dim(), _lib.dims(grad_dist2.shape), idx2.dim(), _lib.dims(idx2.shape)))
+    xyz1 = _prep(xyz1, torch.float32, "xyz1")
+    xyz2 = _prep(xyz2, torch.float32, "xyz2")
+    grad_dist1 = _prep(grad_dist1, torch.float32, "grad_dist1")
+    grad_dist2 = _prep(grad_dist2, torch.float32, "grad_dist2")
+    idx1 = _prep(idx1, torch.int32, "idx1")
+    idx2 = _prep(idx2, torch.int32, "idx2")
+    dev = _same_device(xyz1, xyz2, grad_dist1, grad_dist2, idx1, idx2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    g1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+    g2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+    if dev.type == "cuda":
+        with _Guard(dev):
+            rc = lib.ga_nn_distance_bwd(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), grad_dist1.data_ptr(),
+                                        idx1.data_ptr(), grad_dist2.data_ptr(), idx2.data_ptr(), g1.data_ptr(),
+                                        g2.data_ptr(), _stream(xyz1))
+    else:
+        rc = lib.ga_nn_distance_bwd_host(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), grad_dist1.data_ptr(),
+                                         idx1.data_ptr(), grad_dist2.data_ptr(), idx2.data_ptr(), g1.data_ptr(),
+                                         g2.data_ptr())
+    _lib.check(rc)
+    return g1, g2
+
+
+class _NnDistanceFn(torch.autograd.Function):
+    """Autograd glue: gradient only through dist1/dist2, idx non-differentiable
+    (tf_nndistance.py:35-41; dist_chamfer_3D.py:49-64)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, mode):
+        dist1, idx1, dist2, idx2 = _nn_distance_fwd(xyz1, xyz2, mode)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, idx1, dist2, idx2
+
+    @staticmethod
+    def backward(ctx, grad_dist1, grad_idx1, grad_dist2, grad_idx2):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        if grad_dist1 is None:
+            grad_dist1 = torch.zeros(idx1.shape, dtype=torch.float32, device=idx1.device)
+        if grad_dist2 is None:
+            grad_dist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=idx2.device)
+        g1, g2 = nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2)
+        return g1, g2, None
+
+
+def nn_distance(xyz1, xyz2, mode=None):
+    """Nearest-neighbour distances for a pair of batched clouds (tf_nndistance.py:15-26).
+
+    xyz1 (B,N,3), xyz2 (B,M,3) float32 -> dist1 (B,N) squared distance from each point of
+    xyz1 to its nearest point of xyz2, idx1 (B,N) int32 its index, dist2 / idx2 the other
+    way.  Lowest index wins ties.  Differentiable through dist1 / dist2."""
+    mode = _default_mode if mode is None else mode
+    if not (torch.is_grad_enabled() and (xyz1.requires_grad or xyz2.requires_grad)):
+        return _nn_distance_fwd(xyz1, xyz2, mode)
+    return _NnDistanceFn.apply(xyz1, xyz2, mode)
+
+
+class chamfer_3DFunction(torch.autograd.Function):
+    """dist_chamfer_3D.py:26-64 -- same op, torch return order (dist1, dist2, idx1, idx2)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        dist1, idx1, dist2, idx2 = _nn_distance_fwd(xyz1, xyz2, _default_mode)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        if graddist1 is None:
+            graddist1 = torch.zeros(idx1.shape, dtype=torch.float32, device=idx1.device)
+        if graddist2 is None:
+            graddist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=idx2.device)
+        return nn_distance_grad(xyz1, xyz2, graddist1, idx1, graddist2, idx2)
+
+
+class chamfer_3DDist(torch.nn.Module):
+    """Drop-in for AtlasNet's chamfer_3DDist (dist_chamfer_3D.py:66-74)."""
+
+    def forward(self, input1, input2):
+        input1 = input1.contiguous()
+        input2 = input2.contiguous()
+        return chamfer_3DFunction.apply(input1, input2)
+
+
+def chamfer_per_cloud(dist1, dist2):
+    """mean(dist1,1) + mean(dist2,1) per cloud (src/adv_ae.py:120-121), one fused reduction."""
+    lib = _lib.load()
+    dist1 = _prep(dist1, torch.float32, "dist1")
+    dist2 = _prep(dist2, torch.float32, "dist2")
+    dev = _same_device(dist1, dist2)
+    if dev.type != "cuda":
+        raise ValueError("chamfer_per_cloud expects CUDA tensors")
+    b, n = dist1.shape
+    m = dist2.shape[1]
+    out = torch.empty((b,), dtype=torch.float32, device=dev)
+    with _Guard(dev):
+        _lib.check(lib.ga_chamfer_per_cloud(b, n, m, dist1.data_ptr(), dist2.data_ptr(), out.data_ptr(),
+                                            _stream(dist1)))
+    return out
+
+
+def chamfer_all_pairs(clouds, row0=0, rows=None, mode=None):
+    """Rows [row0, row0+rows) of the all-pairs Chamfer matrix of
+    attacker/prepare_indices_for_attack.py:104-139: out[r, j] = CD(source=clouds[j],
+    target=clouds[row0+r])."""
+    lib = _lib.load()
+    clouds = _prep(clouds, torch.float32, "clouds")
+    if clouds.dim() != 3 or clouds.shape[2] != 3:
+        raise ValueError("clouds must be (S,N,3)")
+    if clouds.device.type != "cuda":
+        raise ValueError("chamfer_all_pairs expects a CUDA tensor")
+    s, n, _ = clouds.shape
+    rows = s - row0 if rows is None else rows
+    if row0 < 0 or rows < 0 or row0 + rows > s:
+        raise ValueError("row block [%d, %d) outside 0..%d" % (row0, row0 + rows, s))
+    out = torch.empty((rows, s), dtype=torch.float32, device=clouds.device)
+    mode = _default_mode if mode is None else mode
+    with _Guard(clouds.device):
+        _lib.check(lib.ga_chamfer_all_pairs(s, n, clouds.data_ptr(), row0, rows, out.data_ptr(), mode,
+                                            _stream(clouds)))
+    return out
+
+
+# --------------------------------------------------------------------------- grouping
+def knn_point(k, xyz1, xyz2):
+    """k nearest neighbours (tf_grouping.py:48-75).  xyz1 (B,N,3) data set, xyz2 (B,M,3)
+    queries -> val (B,M,k) squared distances ascending, idx (B,M,k) int32 into xyz1, with
+    the tie behaviour of the reference's selection sort.  No gradient (ops.NoGradient)."""
+    lib = _lib.load()
+    xyz1 = _prep(xyz1.detach(), torch.float32, "xyz1")
+    xyz2 = _prep(xyz2.detach(), torch.float32, "xyz2")
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[2] != 3 or xyz2.shape[2] != 3:
+        raise ValueError("knn_point expects (batch_size, ndataset, 3) xyz1 and (batch_size, npoint, 3) xyz2")
+    if xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("knn_point expects xyz1 and xyz2 have same batch size")
+    dev = _same_device(xyz1, xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    k = int(k)
+    val = torch.empty((b, m, max(k, 0)), dtype=torch.float32, device=dev)
+    idx = torch.empty((b, m, max(k, 0)), dtype=torch.int32, device=dev)
+    if dev.type == "cuda":
+        with _Guard(dev):
+            rc = lib.ga_knn(b, n, m, k, xyz1.data_ptr(), xyz2.data_ptr(), val.data_ptr(), idx.data_ptr(),
+                            _stream(xyz1))
+    else:
+        rc = lib.ga_knn_host(b, n, m, k, xyz1.data_ptr(), xyz2.data_ptr(), val.data_ptr(), idx.data_ptr())
+    _lib.check(rc)
+    return val, idx
+
+
+def select_top_k(k, dist):
+    """Legacy dense entry (tf_grouping.py:22-31): dist (b,m,n) -> idx (b,m,n), dist_out (b,m,n);
+    the first k columns hold the k smallest, selection-sort order."""
+    lib = _lib.load()
+    _lib.check(lib.ga_check_selection_sort(int(k), dist.dim(), _lib.dims(dist.shape)))
+    dist = _prep(dist.detach(), torch.float32, "dist")
+    if dist.device.type != "cuda":
+        raise ValueError("select_top_k expects a CUDA tensor (the reference op has GPU kernels only, "
+                         "tf_grouping.cpp:139)")
+    b, m, n = dist.shape
+    outi = torch.empty((b, m, n), dtype=torch.int32, device=dist.device)
+    out = torch.empty((b, m, n), dtype=torch.float32, device=dist.device)
+    with _Guard(dist.device):
+        _lib.check(lib.ga_selection_sort(b, n, m, int(k), dist.data_ptr(), outi.data_ptr(), out.data_ptr(),
+                                         _stream(dist)))
+    return outi, out
+
+
+class _GroupPointFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        lib = _lib.load()
+        b, n, c = points.shape
+        _, m, ns = idx.shape
+        out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
+        with _Guard(points.device):
+            _lib.check(lib.ga_group_point(b, n, c, m, ns, points.data_ptr(), idx.data_ptr(), out.data_ptr(),
+                                          _stream(points)))
+        ctx.save_for_backward(idx)
+        ctx.shape = (b, n, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        # GroupPointGrad (tf_grouping_g.cu:61-78) is a scatter-add; no script differentiates through
+        # group_point, so this off-path gradient uses torch's index_add_.
+        (idx,) = ctx.saved_tensors
+        b, n, c = ctx.shape
+        g = torch.zeros((b * n, c), dtype=grad_out.dtype, device=grad_out.device)
+        flat = (idx.long() + torch.arange(b, device=idx.device).view(b, 1, 1) * n).reshape(-1)
+        g.index_add_(0, flat, grad_out.reshape(-1, c))
+        return g.view(b, n, c), None
+
+
+def group_point(points, idx):
+    """out[b,j,s,:] = points[b, idx[b,j,s], :] (tf_grouping.py:33-47)."""
+    lib = _lib.load()
+    _lib.check(lib.ga_check_group_point(points.dim(), _lib.dims(points.shape), idx.dim(), _lib.dims(idx.shape)))
+    points = _prep(points, torch.float32, "points")
+    idx = _prep(idx, torch.int32, "idx")
+    dev = _same_device(points, idx)
+    if dev.type != "cuda":
+        raise ValueError("group_point expects CUDA tensors (the reference op has GPU kernels only, "
+                         "tf_grouping.cpp:171)")
+    return _GroupPointFn.apply(points, idx)
+
+
+def knn_dists(pc, k):
+    """Per-point distances to the k nearest other points, (B,N,k) float32: the graph of
+    defender/get_knn_dists_per_point.py:78-81 (knn_point(k+1) -> drop self -> group_point ->
+    subtract centre -> sqrt(sum(sq))) as one kernel."""
+    lib = _lib.load()
+    pc = _prep(pc.detach(), torch.float32, "pc")
+    if pc.dim() != 3 or pc.shape[2] != 3:
+        raise ValueError("knn_dists expects (batch_size, num_points, 3)")
+    b, n, _ = pc.shape
+    k = int(k)
+    out = torch.empty((b, n, max(k, 0)), dtype=torch.float32, device=pc.device)
+    if pc.device.type == "cuda":
+        with _Guard(pc.device):
+            rc = lib.ga_knn_dists(b, n, k, pc.data_ptr(), out.data_ptr(), _stream(pc))
+    else:
+        rc = lib.ga_knn_dists_host(b, n, k, pc.data_ptr(), out.data_ptr())
+    _lib.check(rc)
+    return out

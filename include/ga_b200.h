@@ -1,0 +1,152 @@
+/* ga_b200.h -- C ABI of the B200-native Chamfer / kNN hot path of geometric_adv.
+ *
+ * One shared library, libga_b200.so (geometric_adv_b200/csrc/), hand-written
+ * CUDA for sm_100a.  Plain pointers and sizes only: no torch / TensorFlow types.
+ * Every entry point names the reference interface it replaces (path:line below
+ * the reference tree); INTEGRATION.md shows the binding a maintainer adds on
+ * the reference side.
+ *
+ * Conventions (reference conventions kept unless noted):
+ *   - fp32 row-major contiguous clouds (B,N,3), int32 indices.
+ *   - The caller allocates every output (the reference ops use
+ *     allocate_output, tf_nndistance.cpp:191-196); kernels never allocate.
+ *     Inputs are read only.  Outputs are fully overwritten (no pre-zeroing
+ *     needed, unlike chamfer3D.cu:177-178).
+ *   - `*_fwd`, `*_bwd`, ga_knn, ... take DEVICE pointers and a cudaStream_t and
+ *     only enqueue work (CUDA-graph capturable).  The `*_host` twins take HOST
+ *     pointers, stage through pinned buffers and return when results are in the
+ *     caller's memory: they are the drop-in for the reference's CPU-tensor
+ *     kernels (REGISTER_KERNEL_BUILDER(...DEVICE_CPU), tf_nndistance.cpp:83,166).
+ *   - Return value: GA_OK (0); a negative GA_ERR_* for argument errors; or a
+ *     positive cudaError_t.  ga_last_error() gives the message for the calling
+ *     thread.  (The reference does no CUDA error checking, chamfer3D.cu:145-151
+ *     only printf()s.)
+ *   - Re-entrant; no global mutable state except the per-thread error string and
+ *     a per-thread pinned staging arena used by the *_host entry points.
+ */
+#ifndef GA_B200_H_
+#define GA_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* ga_stream_t; /* == cudaStream_t */
+
+enum {
+  GA_OK = 0,
+  GA_ERR_INVALID_ARGUMENT = -1, /* shape / attr rejected, same conditions as the reference OP_REQUIRES */
+  GA_ERR_UNSUPPORTED = -2,      /* valid for the reference but outside what this build handles */
+  GA_ERR_NO_DEVICE = -3         /* no sm_100 device / driver */
+};
+
+/* Arithmetic of the squared distance (bit-level contract):
+ *   GA_MODE_CPU_EXACT  ((x*x)+(y*y))+(z*z), unfused, x = target - query: bit-identical
+ *                      to nnsearch, tf_nndistance.cpp:21-43 (g++ -O2).      [default]
+ *   GA_MODE_GPU_REF    fma(z,z,fma(x,x,y*y)): bit-identical to the reference's
+ *                      NmDistanceKernel (tf_nndistance_g.cu:5-127 == chamfer3D.cu:12-134)
+ *                      as nvcc compiles it for sm_100a.
+ * Both have the same speed: the scan runs on a cheaper filter and only the
+ * surviving candidates are evaluated in the selected arithmetic. */
+enum { GA_MODE_CPU_EXACT = 0, GA_MODE_GPU_REF = 1 };
+
+int ga_version(void);
+const char* ga_last_error(void);
+/* Number of kernels this library has launched from the calling process so far
+ * (bench.py's gpu_launches). */
+long long ga_launch_count(void);
+
+/* ---- argument checks with the reference's own messages ------------------- */
+/* tf_nndistance.cpp:51-58 (NnDistance), :91-104 (NnDistanceGrad; pass the four
+ * extra ranks/dims, or rank -1 to skip them).  Returns GA_OK or
+ * GA_ERR_INVALID_ARGUMENT with the reference's message in ga_last_error(). */
+int ga_check_nn_distance(int rank1, const long long* dims1, int rank2, const long long* dims2);
+int ga_check_nn_distance_grad(int rank1, const long long* dims1, int rank2, const long long* dims2,
+                              int rank_gd1, const long long* dims_gd1, int rank_idx1, const long long* dims_idx1,
+                              int rank_gd2, const long long* dims_gd2, int rank_idx2, const long long* dims_idx2);
+/* tf_grouping.cpp:112-118 (SelectionSort: k>0, rank 3), :149-155 (GroupPoint). */
+int ga_check_selection_sort(int k, int rank, const long long* dims);
+int ga_check_group_point(int rank_points, const long long* dims_points, int rank_idx, const long long* dims_idx);
+
+/* ---- Chamfer: nn_distance and its gradient -------------------------------- */
+/* Replaces NmDistanceKernelLauncher (tf_nndistance.cpp:168, tf_nndistance_g.cu:128-131)
+ * and chamfer_cuda_forward (chamfer_cuda.cpp:9, chamfer3D.cu:136-154), and, through the
+ * _host twin, NnDistanceOp's CPU path (tf_nndistance.cpp:45-83).
+ * dist1/idx1 (b,n): for each point of xyz1 the squared distance to / index of its
+ * nearest point of xyz2 (lowest index on ties); dist2/idx2 (b,m): the other way. */
+int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1, int* idx1,
+                       float* dist2, int* idx2, int mode, ga_stream_t stream);
+int ga_nn_distance_fwd_host(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1, int* idx1,
+                            float* dist2, int* idx2, int mode);
+
+/* Replaces NmDistanceGradKernelLauncher (tf_nndistance.cpp:208, tf_nndistance_g.cu:152-157),
+ * chamfer_cuda_backward (chamfer_cuda.cpp:12, chamfer3D.cu:176-195) and
+ * NnDistanceGradOp's CPU loops (tf_nndistance.cpp:122-163).  Atomic-free: every
+ * output element is accumulated by one thread in exactly the CPU loop order, so
+ * the result is bit-identical to the CPU reference and run-to-run reproducible. */
+int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const float* xyz2, const float* grad_dist1,
+                       const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1,
+                       float* grad_xyz2, ga_stream_t stream);
+int ga_nn_distance_bwd_host(int b, int n, int m, const float* xyz1, const float* xyz2, const float* grad_dist1,
+                            const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1,
+                            float* grad_xyz2);
+
+/* Forward + backward in one host call (what one training / attack step does
+ * with the op): HOST buffers in, HOST buffers out, one H2D and one D2H leg. */
+int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const float* xyz2,
+                                const float* grad_dist1, const float* grad_dist2, float* dist1, int* idx1,
+                                float* dist2, int* idx2, float* grad_xyz1, float* grad_xyz2, int mode);
+
+/* Per-cloud Chamfer scalar, out[i] = mean(dist1[i,:]) + mean(dist2[i,:]): the reduction
+ * the scripts apply to the op's outputs (src/adv_ae.py:120-121,
+ * attacker/prepare_indices_for_attack.py:113-114).  Fixed summation tree => reproducible. */
+int ga_chamfer_per_cloud(int b, int n, int m, const float* dist1, const float* dist2, float* out,
+                         ga_stream_t stream);
+
+/* All-pairs driver of attacker/prepare_indices_for_attack.py:104-139: `clouds` (s,n,3);
+ * out (rows,s) with out[r, j] = CD(source = clouds[j], target = clouds[row0 + r]) as in
+ * :139,151.  Row blocks are the multi-GPU shard unit. */
+int ga_chamfer_all_pairs(int s, int n, const float* clouds, int row0, int rows, float* out, int mode,
+                         ga_stream_t stream);
+
+/* ---- grouping: knn_point / selection_sort / group_point ------------------- */
+/* knn_point(k, xyz1, xyz2) of tf_grouping.py:48-75 in ONE kernel: xyz1 (b,n,3) is the
+ * data set, xyz2 (b,m,3) the queries; val/idx (b,m,k): the k smallest squared distances
+ * ((dx*dx+dy*dy)+dz*dz, dx = xyz1 - xyz2) in ascending order and their indices into
+ * xyz1, with exactly the tie behaviour of the reference's selection sort
+ * (tf_grouping_g.cu:83-123).  Deliberate ABI change: no dense (b,m,n) matrix. */
+int ga_knn(int b, int n, int m, int k, const float* xyz1, const float* xyz2, float* val, int* idx,
+           ga_stream_t stream);
+int ga_knn_host(int b, int n, int m, int k, const float* xyz1, const float* xyz2, float* val, int* idx);
+
+/* Legacy dense entry, replaces selectionSortLauncher (tf_grouping.cpp:108,
+ * tf_grouping_g.cu:129-132): dist (b,m,n) -> outi, out (b,m,n); the first k columns of
+ * every row are the selection-sort result, the remaining columns hold the rest of the
+ * row exactly as the reference leaves it. */
+int ga_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out,
+                      ga_stream_t stream);
+
+/* Replaces groupPointLauncher (tf_grouping.cpp:142, tf_grouping_g.cu:133-136):
+ * out[b,j,s,:] = points[b, idx[b,j,s], :]. */
+int ga_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx, float* out,
+                   ga_stream_t stream);
+
+/* defender/get_knn_dists_per_point.py:78-81 fused: knn_point(k+1, pc, pc), drop the
+ * first neighbour, gather, subtract the centre, sqrt(sum(delta^2)) -> out (b,n,k). */
+int ga_knn_dists(int b, int n, int k, const float* pc, float* out, ga_stream_t stream);
+int ga_knn_dists_host(int b, int n, int k, const float* pc, float* out);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* Dependent-free FFMA loop on every SM; returns achieved FP32 TFLOP/s (2 flop per
+ * FFMA lane) through *tflops.  bench.py uses it as the FP32 roofline denominator,
+ * since MEASURED_PEAKS.json holds HBM and BF16 only. */
+int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
+/* Tuning hook for benchmarks: key 0 selects the forward-kernel tile variant (0 = default). */
+int ga_set_tuning(int key, int value);
+/* Empty-kernel launch floor in microseconds (average over `reps` launches). */
+int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GA_B200_H_ */

@@ -1,0 +1,143 @@
+"""GPU parity of the grouping ops: knn_point, select_top_k, group_point, knn_dists."""
+import numpy as np
+import pytest
+import torch
+
+from util import bits_equal, cloud
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def check_knn(ga, oracle, k, xyz1, xyz2):
+    val, idx = ga.knn_point(k, t(xyz1), t(xyz2))
+    wv, wi = oracle.knn_point(k, xyz1, xyz2)
+    val, idx = val.cpu().numpy(), idx.cpu().numpy()
+    assert bits_equal(val, wv), "val: %d mismatches" % int(np.sum(val != wv))
+    assert np.array_equal(idx, wi), "idx: %d mismatches (k=%d, %s vs %s)" % (
+        int(np.sum(idx != wi)), k, xyz1.shape, xyz2.shape)
+
+
+@pytest.mark.parametrize("k", [1, 2, 8, 11, 16, 17, 32])
+@pytest.mark.parametrize("shape", [(2, 512, 128), (1, 2048, 300), (1, 100, 33), (1, 2500, 64), (1, 5000, 40)])
+def test_knn_point_bit_exact(ga, oracle, k, shape):
+    b, n, m = shape
+    check_knn(ga, oracle, k, cloud(600 + n, (b, n, 3)), cloud(700 + m, (b, m, 3)))
+
+
+def test_knn_self_query_defense_shape(ga, oracle):
+    """get_knn_dists_per_point.py:78: knn_point(k+1, pc, pc) with k+1 = 11 on 2048-point clouds."""
+    pc = cloud(4, (3, 2048, 3))
+    check_knn(ga, oracle, 11, pc, pc)
+    check_knn(ga, oracle, 9, pc, pc)  # the script's default num_knn = 8
+
+
+@pytest.mark.parametrize("k", [1, 3, 11, 16, 20])
+def test_knn_tie_semantics_of_the_selection_sort(ga, oracle, k):
+    """Coordinates on a coarse grid and duplicated points: exact ties everywhere.  Indices must
+    follow the reference's unstable selection sort (tf_grouping_g.cu:100-121), not a stable sort."""
+    rng = np.random.default_rng(k)
+    data = (rng.integers(0, 3, (2, 400, 3)).astype(np.float32) * np.float32(0.5))
+    qry = (rng.integers(0, 3, (2, 90, 3)).astype(np.float32) * np.float32(0.5))
+    check_knn(ga, oracle, k, data, qry)
+    pc = cloud(5, (1, 600, 3))
+    pc[0, 300:] = pc[0, :300]          # every point duplicated once
+    check_knn(ga, oracle, k, pc, pc)
+    z = np.zeros((1, 64, 3), np.float32)
+    check_knn(ga, oracle, k, z, z)     # all distances equal
+
+
+def test_knn_k_equals_n_and_small_sets(ga, oracle):
+    check_knn(ga, oracle, 5, cloud(1, (2, 5, 3)), cloud(2, (2, 9, 3)))
+    check_knn(ga, oracle, 1, cloud(3, (1, 1, 3)), cloud(4, (1, 3, 3)))
+    check_knn(ga, oracle, 12, cloud(5, (1, 12, 3)), cloud(6, (1, 40, 3)))
+
+
+def test_knn_large_k_generic_path(ga, oracle):
+    """tf_grouping.py:86-90 self-test shape: 512 data points, 128 queries, nsample 64."""
+    check_knn(ga, oracle, 64, cloud(7, (2, 512, 3), 0.0, 1.0), cloud(8, (2, 128, 3), 0.0, 1.0))
+    check_knn(ga, oracle, 40, cloud(9, (1, 100, 3)), cloud(10, (1, 50, 3)))
+
+
+def test_knn_argument_errors(ga):
+    x = t(cloud(1, (1, 10, 3)))
+    with pytest.raises(ValueError, match="positive k"):
+        ga.knn_point(0, x, x)
+    with pytest.raises(ValueError, match="exceeds the data set size"):
+        ga.knn_point(11, x, x)
+
+
+def test_knn_non_finite(ga, oracle):
+    data, qry = cloud(11, (1, 200, 3)), cloud(12, (1, 50, 3))
+    data[0, 150, 1] = np.nan   # NaN beyond the first k positions: never selected
+    data[0, 160, 0] = np.inf
+    check_knn(ga, oracle, 6, data, qry)
+    data[0, 2, 2] = np.nan     # NaN inside the first k positions: "selected" by the reference
+    check_knn(ga, oracle, 6, data, qry)
+    qry[0, 7, 0] = np.nan
+    check_knn(ga, oracle, 6, data, qry)
+
+
+def test_knn_dists_equals_numpy_fallback_path(ga, oracle):
+    """(B,N,k) distances, bitwise equal to defender/get_knn_dists_per_point.py:125-137 (numpy path)
+    and to the op graph :78-81 restated in the oracle."""
+    pc = cloud(4, (4, 2048, 3))
+    got = ga.knn_dists(t(pc), 10).cpu().numpy()
+    assert bits_equal(got, oracle.knn_dists(pc, 10))
+    assert bits_equal(got[:2], oracle.knn_dists_numpy(pc[:2], 10))
+    host = ga.knn_dists(torch.from_numpy(pc), 10).numpy()
+    assert bits_equal(got, host)
+    assert np.all(got >= 0)
+
+
+def test_knn_dists_full_size_properties(ga):
+    """B=500 (config 5): ascending per point, self-distance dropped, shard == whole."""
+    pc = cloud(4, (500, 2048, 3))
+    out = ga.knn_dists(t(pc), 10)
+    assert out.shape == (500, 2048, 10)
+    assert bool(torch.all(out[..., 1:] >= out[..., :-1])) and bool(torch.all(out > 0))
+    part = ga.knn_dists(t(pc[62:125]), 10)
+    assert torch.equal(part, out[62:125])
+
+
+def test_script_graph_equals_fused_kernel(ga):
+    """The reference graph, op by op, through the shim: knn_point -> idx[:,:,1:] -> group_point ->
+    deltas -> sqrt(sum(sq)) equals knn_dists."""
+    pc = t(cloud(13, (2, 1024, 3)))
+    k = 8
+    _, idx = ga.knn_point(k + 1, pc, pc)
+    grouped = ga.group_point(pc, idx[:, :, 1:].contiguous())
+    deltas = grouped - pc.unsqueeze(2)
+    sq = deltas * deltas
+    d = torch.sqrt((sq[..., 0] + sq[..., 1]) + sq[..., 2])
+    assert torch.equal(d, ga.knn_dists(pc, k))
+
+
+def test_select_top_k_dense_entry(ga, oracle):
+    rng = np.random.default_rng(3)
+    dist = rng.random((3, 17, 130), dtype=np.float32)
+    dist[0, :, ::3] = 0.25  # ties
+    dist[1, 2, 5] = np.nan
+    dist[1, 3, 0] = np.nan  # NaN head stays selected
+    for k in [1, 4, 16, 130]:
+        outi, out = ga.select_top_k(k, t(dist))
+        wi, wo = oracle.selection_sort(dist, k)
+        assert np.array_equal(outi.cpu().numpy(), wi) and bits_equal(out.cpu().numpy(), wo), k
+
+
+def test_group_point(ga, oracle):
+    rng = np.random.default_rng(4)
+    pts = rng.random((3, 50, 7), dtype=np.float32)
+    idx = rng.integers(0, 50, (3, 20, 6)).astype(np.int32)
+    got = ga.group_point(t(pts), t(idx)).cpu().numpy()
+    assert np.array_equal(got, oracle.group_point(pts, idx))
+    p = t(pts).requires_grad_(True)
+    ga.group_point(p, t(idx)).sum().backward()  # tf_grouping_op_test.py checks this gradient
+    cnt = np.zeros((3, 50), np.float32)
+    for b in range(3):
+        np.add.at(cnt[b], idx[b].reshape(-1), 1.0)
+    np.testing.assert_allclose(p.grad.cpu().numpy(), np.repeat(cnt[..., None], 7, axis=2), rtol=1e-6)
