@@ -10,6 +10,7 @@
 namespace ga {
 
 extern int g_fwd_variant;  // nn_distance_fwd.cu
+extern int g_knn_variant;  // grouping.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -78,6 +79,10 @@ int ga_version(void) { return 100; }
 int ga_set_tuning(int key, int value) {
   if (key == 0) {
     ga::g_fwd_variant = value;
+    return GA_OK;
+  }
+  if (key == 1) {
+    ga::g_knn_variant = value;
     return GA_OK;
   }
   ga::set_error("ga_set_tuning: unknown key %d", key);

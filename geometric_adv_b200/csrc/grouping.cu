@@ -7,15 +7,15 @@
 // O(n + k) memory per query.
 //
 // Algorithm (same filter as nn_distance_fwd.cu, f(q,t) = |t|^2 - 2 q.t):
-//   pass A  FFMA2/FMNMX3 filter scan; minima per 32-point tile go to shared memory,
-//           minima per group of tiles feed a (k+1)-entry sorted list whose last
-//           entry tau bounds the (k+1)-th smallest filter value from above
-//           (k+1 different groups each hold a point with f <= tau).
-//   pass B  only tiles with minimum <= tau + W are rescanned; points with
-//           f <= tau + W are evaluated in the reference arithmetic
+//   pass A  FFMA2/FMNMX3 filter scan; minima per group of tiles feed a (k+1)-entry
+//           sorted list whose last entry tau bounds the (k+1)-th smallest filter
+//           value from above (k+1 different groups each hold a point with f <= tau).
+//   pass B1 second filter scan: points with f <= tau + W (about k+4 per query) are
+//           appended to a per-query queue in shared memory, branch-free.
+//   pass B2 the queued points are evaluated in the reference arithmetic
 //           ((dx*dx+dy*dy)+dz*dz, dx = data - query) and inserted into an exact,
-//           sorted (k+1)-entry list.  W is the rounding window of the filter, so the
-//           exact k+1 nearest are always among the candidates.
+//           sorted (k+1)-entry list, all lanes in step.  W is the rounding window of
+//           the filter, so the exact k+1 nearest are always among the candidates.
 //   ties    the reference's selection sort is unstable on exact ties.  If the exact
 //           list shows a tie (or NaN / missing entries), the query is replayed by a
 //           warp that simulates the selection sort on the only elements that can
@@ -27,10 +27,17 @@ namespace ga {
 // ---------------------------------------------------------------------------
 // Exact replay of the reference selection sort for one query, by one warp.
 // pts: data set (n points), q: query, vk: k-th smallest exact squared distance.
-// cv/ci: shared scratch, >= 3k entries.  Writes k values / indices.
+// cv/ci: shared scratch, >= 3k entries; on return cv[0..k) / ci[0..k) hold the
+// reference's first k columns.
+//
+// Only these elements can take part in the first k rounds of the selection sort:
+// positions < k (they get displaced), values < v_k (they get selected), and the
+// first k elements at positions >= k with value == v_k (selected in position
+// order).  Everything else is never selected and never moved, so the literal sort
+// on the compacted row gives the reference's result.
 // ---------------------------------------------------------------------------
 __device__ void selection_replay(const float* __restrict__ pts, int n, float qx, float qy, float qz, int k,
-                                 float vk, float* cv, int* ci, float* val_out, int* idx_out, int lane) {
+                                 float vk, float* cv, int* ci, int lane) {
   const unsigned lt_mask = (1u << lane) - 1u;
   int cnt = 0, eqcnt = 0;
   for (int base = 0; base < n; base += 32) {
@@ -66,258 +73,18 @@ __device__ void selection_replay(const float* __restrict__ pts, int n, float qx,
       ci[mn] = ci[s];
       cv[s] = tv;
       ci[s] = ti;
-      val_out[s] = tv;
-      idx_out[s] = ti;
     }
   }
   __syncwarp();
 }
 
-struct KnnArgs {
-  int b, n, m, k;      // k = neighbours searched (already k+1 for the defense epilogue)
-  const float* xyz1;   // data set (b,n,3)
-  const float* xyz2;   // queries  (b,m,3)
-  float* val;          // (b,m,k-skip)
-  int* idx;            // (b,m,k-skip) or nullptr
-  int skip;            // leading neighbours dropped (defense: 1)
-  int do_sqrt;         // defense: sqrt of the squared distance
-  int qtiles;          // query tiles per cloud
-};
-
-template <int THREADS, int Q, int T, int CH, int KL>
-struct KnnCfg {
-  static constexpr int kThreads = THREADS, kQ = Q, kQT = THREADS * Q, kT = T, kCH = CH, kKL = KL;
-  static constexpr int kTiles = CH / T;
-  static constexpr int kWarps = THREADS / 32;
-  // tgt | pad | red[32] | tmin[tiles][QT] | flag_q[QT] | flag_vk[QT] | flag_cnt | replay scratch per warp
-  static constexpr size_t kOffRed = (size_t)CH * 16 + (size_t)kPipeU * 32;
-  static constexpr size_t kOffTmin = kOffRed + 32 * 4;
-  static constexpr size_t kOffFlagQ = kOffTmin + (size_t)kTiles * kQT * 4;
-  static constexpr size_t kOffFlagV = kOffFlagQ + (size_t)kQT * 4;
-  static constexpr size_t kOffCnt = kOffFlagV + (size_t)kQT * 4;
-  static constexpr size_t kOffScratch = kOffCnt + 16;
-  static constexpr size_t kSmem = kOffScratch + (size_t)kWarps * 3 * KL * 8;
-};
-
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
-  constexpr int THREADS = Cfg::kThreads, Q = Cfg::kQ, QT = Cfg::kQT, T = Cfg::kT, CH = Cfg::kCH, KL = Cfg::kKL;
+// k-th smallest exact squared distance of one query by k rounds of "next smallest
+// (value, position)", one warp.  O(k n); used when the fast path cannot decide.
+__device__ float kth_smallest_warp(const float* __restrict__ pts, int n, float qx, float qy, float qz, int k,
+                                   int lane) {
   const float kInf = __int_as_float(0x7f800000);
-  extern __shared__ float4 smem_f4[];
-  unsigned char* smem_raw = reinterpret_cast<unsigned char*>(smem_f4);
-  float4* tgt = smem_f4;
-  float* red = reinterpret_cast<float*>(smem_raw + Cfg::kOffRed);
-  float* tmin = reinterpret_cast<float*>(smem_raw + Cfg::kOffTmin);
-  int* flag_q = reinterpret_cast<int*>(smem_raw + Cfg::kOffFlagQ);
-  float* flag_vk = reinterpret_cast<float*>(smem_raw + Cfg::kOffFlagV);
-  int* flag_cnt = reinterpret_cast<int*>(smem_raw + Cfg::kOffCnt);
-  unsigned char* scratch = smem_raw + Cfg::kOffScratch;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int batch = blockIdx.x / a.qtiles;
-  const int qtile = blockIdx.x - batch * a.qtiles;
-  const int n = a.n, k = a.k;
-  const float* pts = a.xyz1 + (size_t)batch * n * 3;
-  const float* qpts = a.xyz2 + (size_t)batch * a.m * 3;
-  const int kout = k - a.skip;
-  if (tid == 0) *flag_cnt = 0;
-
-  float qx[Q], qy[Q], qz[Q], qabs[Q], ax2[Q], ay2[Q], az2[Q];
-  bool valid[Q], replay[Q];
-#pragma unroll
-  for (int j = 0; j < Q; j++) {
-    const int qi = qtile * QT + j * THREADS + tid;
-    valid[j] = qi < a.m;
-    const int qs = valid[j] ? qi : 0;
-    qx[j] = __ldg(qpts + (size_t)qs * 3);
-    qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
-    qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
-    qabs[j] = query_abs(qx[j], qy[j], qz[j]);
-    ax2[j] = -2.0f * qx[j];
-    ay2[j] = -2.0f * qy[j];
-    az2[j] = -2.0f * qz[j];
-    // A NaN distance at a position < k is "selected" by the reference (nothing compares
-    // below NaN): only the replay reproduces that.
-    bool nan_low = false;
-    for (int i = 0; i < k; i++) {
-      const float d = sqdist<GA_MODE_CPU_EXACT>(__ldg(pts + (size_t)i * 3), __ldg(pts + (size_t)i * 3 + 1),
-                                                __ldg(pts + (size_t)i * 3 + 2), qx[j], qy[j], qz[j]);
-      nan_low |= d != d;
-    }
-    replay[j] = nan_low;
-  }
-
-  // exact sorted lists (value, index), carried across chunks
-  float Lv[Q][KL];
-  int Li[Q][KL];
-#pragma unroll
-  for (int j = 0; j < Q; j++)
-#pragma unroll
-    for (int s = 0; s < KL; s++) {
-      Lv[j][s] = kInf;
-      Li[j][s] = -1;
-    }
-  float tau[Q];
-#pragma unroll
-  for (int j = 0; j < Q; j++) tau[j] = kInf;
-  float bm_run = 0.0f;
-
-  for (int c0 = 0; c0 < n; c0 += CH) {
-    const int cn = min(CH, n - c0);
-    const int ntile = (cn + T - 1) / T;
-    bm_run = fmaxf(bm_run, stage_targets<THREADS, T>(tgt, red, pts, c0, n, ntile, tid));
-
-    // ---- pass A ---------------------------------------------------------------
-    // groups of `tpg` tiles; at least k+1 groups are needed for a finite tau
-    int tpg = ntile / (2 * (k + 1));
-    if (tpg < 1) tpg = 1;
-    float S[Q][KL];  // k+1 smallest group minima of this chunk (only the first k+1 slots are used)
-    float gmin[Q];
-#pragma unroll
-    for (int j = 0; j < Q; j++) {
-      gmin[j] = kInf;
-#pragma unroll
-      for (int s = 0; s < KL; s++) S[j][s] = kInf;
-    }
-    int left = tpg;
-    filter_scan<Q, T>(tgt, ntile, ax2, ay2, az2, [&](int tile, const float(&tm)[Q]) {
-#pragma unroll
-      for (int j = 0; j < Q; j++) {
-        tmin[(size_t)tile * QT + j * THREADS + tid] = tm[j];
-        gmin[j] = fminf(gmin[j], tm[j]);
-      }
-      if (--left == 0 || tile == ntile - 1) {
-        left = tpg;
-#pragma unroll
-        for (int j = 0; j < Q; j++) {
-          float v = gmin[j];
-          gmin[j] = kInf;
-#pragma unroll
-          for (int s = 0; s < KL; s++) {  // sorted insert by compare-exchange chain
-            const float lo = fminf(S[j][s], v);
-            v = fmaxf(S[j][s], v);
-            S[j][s] = lo;
-          }
-        }
-      }
-    });
-
-    // ---- pass B ---------------------------------------------------------------
-#pragma unroll
-    for (int j = 0; j < Q; j++) {
-      if (!valid[j]) continue;
-      // (k+1)-th smallest group minimum; slots beyond k are never read
-      float tk = kInf;
-#pragma unroll
-      for (int s = 0; s < KL; s++)
-        if (s == k) tk = S[j][s];
-      tau[j] = fminf(tau[j], tk);
-      const float thr = tau[j] + filter_window(qabs[j], bm_run);
-      for (int tile = 0; tile < ntile; tile++) {
-        const float tmv = tmin[(size_t)tile * QT + j * THREADS + tid];
-        if (tmv > thr) continue;  // NaN threshold falls through
-        const float4* tp = tgt + (size_t)tile * T;
-        const int g0 = c0 + tile * T;
-#pragma unroll 2
-        for (int pp = 0; pp < T / 2; pp++) {
-          const float4 u = tp[2 * pp];
-          const float4 v = tp[2 * pp + 1];
-          const float2 f = filter_pair(u, v, ax2[j], ay2[j], az2[j]);
-          if (fminf(f.x, f.y) > thr) continue;
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int g = g0 + 2 * pp + h;
-            const float fv = h ? f.y : f.x;
-            if (fv > thr || g >= n) continue;
-            const float d = h ? sqdist<GA_MODE_CPU_EXACT>(u.y, u.w, v.y, qx[j], qy[j], qz[j])
-                              : sqdist<GA_MODE_CPU_EXACT>(u.x, u.z, v.x, qx[j], qy[j], qz[j]);
-            if (d < Lv[j][KL - 1]) {
-              // candidates arrive in ascending index order: a new element goes behind
-              // every stored element with value <= d
-#pragma unroll
-              for (int s = KL - 1; s >= 1; s--) {
-                const bool up = d < Lv[j][s - 1];
-                const bool here = d < Lv[j][s];
-                Li[j][s] = up ? Li[j][s - 1] : (here ? g : Li[j][s]);
-                Lv[j][s] = up ? Lv[j][s - 1] : (here ? d : Lv[j][s]);
-              }
-              if (d < Lv[j][0]) {
-                Lv[j][0] = d;
-                Li[j][0] = g;
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-
-  // ---- output / tie detection -------------------------------------------------
-  const bool need_idx = a.idx != nullptr;
-#pragma unroll
-  for (int j = 0; j < Q; j++) {
-    if (!valid[j]) continue;
-    const int qi = qtile * QT + j * THREADS + tid;
-    bool rp = replay[j];
-    float vk = kInf;
-#pragma unroll
-    for (int s = 0; s < KL; s++) {
-      if (s == k - 1) {
-        vk = Lv[j][s];
-        rp |= Li[j][s] < 0;  // fewer than k finite distances
-      }
-      if (s + 1 < KL && s < k) rp |= (Lv[j][s] == Lv[j][s + 1]) && Li[j][s + 1] >= 0;
-    }
-    if (need_idx && rp) {
-      const int slot = atomicAdd(flag_cnt, 1);
-      flag_q[slot] = j * THREADS + tid;
-      flag_vk[slot] = (Li[j][0] < 0 || vk != vk) ? kInf : vk;
-      continue;
-    }
-    float* vo = a.val + ((size_t)batch * a.m + qi) * kout;
-    int* io = need_idx ? a.idx + ((size_t)batch * a.m + qi) * kout : nullptr;
-#pragma unroll
-    for (int s = 0; s < KL; s++) {
-      if (s >= a.skip && s < k) {
-        vo[s - a.skip] = a.do_sqrt ? __fsqrt_rn(Lv[j][s]) : Lv[j][s];
-        if (need_idx) io[s - a.skip] = Li[j][s];
-      }
-    }
-  }
-  __syncthreads();
-  // ---- replay of flagged queries, one warp each --------------------------------
-  const int nflag = *flag_cnt;
-  float* cv = reinterpret_cast<float*>(scratch + (size_t)warp * 3 * KL * 8);
-  int* ci = reinterpret_cast<int*>(cv + 3 * KL);
-  for (int f = warp; f < nflag; f += THREADS / 32) {
-    const int ql = flag_q[f];
-    const int qi = qtile * QT + ql;
-    const float x = __ldg(qpts + (size_t)qi * 3), y = __ldg(qpts + (size_t)qi * 3 + 1),
-                z = __ldg(qpts + (size_t)qi * 3 + 2);
-    // skip is only used by the value-only defense path, which never replays
-    selection_replay(pts, n, x, y, z, k, flag_vk[f], cv, ci, a.val + ((size_t)batch * a.m + qi) * kout,
-                     a.idx + ((size_t)batch * a.m + qi) * kout, lane);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Generic k (k > 32): one warp per query.  v_k by k rounds of "next smallest
-// (value, position)", then the same replay.  O(k n) per query; rare path.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) knn_generic_kernel(const KnnArgs a) {
-  extern __shared__ float4 smem_f4[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long q = (long long)blockIdx.x * 4 + warp;
-  if (q >= (long long)a.b * a.m) return;
-  const int batch = (int)(q / a.m), qi = (int)(q - (long long)batch * a.m);
-  const int n = a.n, k = a.k;
-  const float* pts = a.xyz1 + (size_t)batch * n * 3;
-  const float* qp = a.xyz2 + ((size_t)batch * a.m + qi) * 3;
-  const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-  const float kInf = __int_as_float(0x7f800000);
-  float pv = -kInf;  // last selected (value, position), lexicographic
+  float pv = -kInf;
   int pp = -1;
-  bool complete = true;
   for (int s = 0; s < k; s++) {
     float bv = kInf;
     int bp = 0x7fffffff;
@@ -339,20 +106,312 @@ __global__ void __launch_bounds__(128) knn_generic_kernel(const KnnArgs a) {
         bp = op;
       }
     }
-    if (bp == 0x7fffffff) {
-      complete = false;
-      break;
-    }
+    if (bp == 0x7fffffff) return kInf;  // fewer than k comparable distances
     pv = bv;
     pp = bp;
   }
-  const float vk = complete ? pv : kInf;
+  return pv;
+}
+
+// Write one query's result from the replay scratch, applying the defense epilogue.
+__device__ __forceinline__ void write_replayed(const float* cv, const int* ci, int k, int skip, int do_sqrt,
+                                               float* vo, int* io, int lane) {
+  for (int s = skip + lane; s < k; s += 32) {
+    vo[s - skip] = do_sqrt ? __fsqrt_rn(cv[s]) : cv[s];
+    if (io) io[s - skip] = ci[s];
+  }
+  __syncwarp();
+}
+
+struct KnnArgs {
+  int b, n, m, k;      // k = neighbours searched (already k+1 for the defense epilogue)
+  const float* xyz1;   // data set (b,n,3)
+  const float* xyz2;   // queries  (b,m,3)
+  float* val;          // (b,m,k-skip)
+  int* idx;            // (b,m,k-skip) or nullptr
+  int skip;            // leading neighbours dropped (defense: 1)
+  int do_sqrt;         // defense: sqrt of the squared distance
+  int qtiles;          // query tiles per cloud
+};
+
+constexpr int kKnnQueue = 32;  // candidate slots per query
+
+template <int THREADS, int Q, int T, int CH, int KL, bool MULTI>
+struct KnnCfg {
+  static constexpr int kThreads = THREADS, kQ = Q, kQT = THREADS * Q, kT = T, kCH = CH, kKL = KL;
+  static constexpr bool kMulti = MULTI;  // data sets larger than CH: lists persist across chunks
+  static constexpr int kTiles = CH / T;
+  static constexpr int kWarps = THREADS / 32;
+  static_assert((T & (T - 1)) == 0, "tile size must be a power of two");
+  // tgt | pad | red[32] | queue[C+1][QT] u16 | flag_q[QT] | flag_vk[QT] | flag_cnt | replay scratch
+  static constexpr size_t kOffRed = (size_t)CH * 16 + (size_t)kPipeU * 32;
+  static constexpr size_t kOffQueue = kOffRed + 32 * 4;
+  static constexpr size_t kOffFlagQ = kOffQueue + (((size_t)(kKnnQueue + 1) * kQT * 2 + 15) & ~(size_t)15);
+  static constexpr size_t kOffFlagV = kOffFlagQ + (size_t)kQT * 4;
+  static constexpr size_t kOffCnt = kOffFlagV + (size_t)kQT * 4;
+  static constexpr size_t kOffScratch = kOffCnt + 16;
+  static constexpr size_t kSmem = kOffScratch + (size_t)kWarps * 3 * KL * 8;
+};
+
+// sorted insert of (d, g) into an ascending (value, index) list held in registers
+template <int KL>
+__device__ __forceinline__ void list_insert(float (&Lv)[KL], int (&Li)[KL], float d, int g) {
+  if (d < Lv[KL - 1] || (d == Lv[KL - 1] && g < Li[KL - 1])) {
+#pragma unroll
+    for (int s = KL - 1; s >= 1; s--) {
+      const bool up = d < Lv[s - 1] || (d == Lv[s - 1] && g < Li[s - 1]);
+      const bool here = d < Lv[s] || (d == Lv[s] && g < Li[s]);
+      Li[s] = up ? Li[s - 1] : (here ? g : Li[s]);
+      Lv[s] = up ? Lv[s - 1] : (here ? d : Lv[s]);
+    }
+    if (d < Lv[0] || (d == Lv[0] && g < Li[0])) {
+      Lv[0] = d;
+      Li[0] = g;
+    }
+  }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
+  constexpr int THREADS = Cfg::kThreads, Q = Cfg::kQ, QT = Cfg::kQT, T = Cfg::kT, CH = Cfg::kCH, KL = Cfg::kKL;
+  constexpr bool MULTI = Cfg::kMulti;
+  constexpr int LQ = MULTI ? Q : 1;  // persistent lists only when chunks have to be merged
+  const float kInf = __int_as_float(0x7f800000);
+  const float kNaN = __int_as_float(0x7fc00000);
+  extern __shared__ float4 smem_f4[];
+  unsigned char* smem_raw = reinterpret_cast<unsigned char*>(smem_f4);
+  float4* tgt = smem_f4;
+  float* red = reinterpret_cast<float*>(smem_raw + Cfg::kOffRed);
+  unsigned short* queue = reinterpret_cast<unsigned short*>(smem_raw + Cfg::kOffQueue);
+  int* flag_q = reinterpret_cast<int*>(smem_raw + Cfg::kOffFlagQ);
+  float* flag_vk = reinterpret_cast<float*>(smem_raw + Cfg::kOffFlagV);
+  int* flag_cnt = reinterpret_cast<int*>(smem_raw + Cfg::kOffCnt);
+  unsigned char* scratch = smem_raw + Cfg::kOffScratch;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int batch = blockIdx.x / a.qtiles;
+  const int qtile = blockIdx.x - batch * a.qtiles;
+  const int n = a.n, k = a.k;
+  const float* pts = a.xyz1 + (size_t)batch * n * 3;
+  const float* qpts = a.xyz2 + (size_t)batch * a.m * 3;
+  const int kout = k - a.skip;
+  const bool need_idx = a.idx != nullptr;
+  if (tid == 0) *flag_cnt = 0;
+
+  float qx[Q], qy[Q], qz[Q], qabs[Q], ax2[Q], ay2[Q], az2[Q];
+  bool valid[Q], replay[Q];
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    const int qi = qtile * QT + j * THREADS + tid;
+    valid[j] = qi < a.m;
+    const int qs = valid[j] ? qi : 0;
+    qx[j] = __ldg(qpts + (size_t)qs * 3);
+    qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
+    qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
+    qabs[j] = query_abs(qx[j], qy[j], qz[j]);
+    ax2[j] = -2.0f * qx[j];
+    ay2[j] = -2.0f * qy[j];
+    az2[j] = -2.0f * qz[j];
+    // A NaN distance at a position < k is "selected" by the reference (nothing compares
+    // below NaN): only the replay reproduces that.
+    bool nan_low = false;
+    if (need_idx)
+      for (int i = 0; i < k; i++) {
+        const float d = sqdist<GA_MODE_CPU_EXACT>(__ldg(pts + (size_t)i * 3), __ldg(pts + (size_t)i * 3 + 1),
+                                                  __ldg(pts + (size_t)i * 3 + 2), qx[j], qy[j], qz[j]);
+        nan_low |= d != d;
+      }
+    replay[j] = nan_low;
+  }
+
+  // exact sorted lists (value, index); persistent across chunks only in the MULTI build
+  float PLv[LQ][KL];
+  int PLi[LQ][KL];
+#pragma unroll
+  for (int j = 0; j < LQ; j++)
+#pragma unroll
+    for (int s = 0; s < KL; s++) {
+      PLv[j][s] = kInf;
+      PLi[j][s] = -1;
+    }
+  float tau[Q];
+  bool overflow[Q];
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    tau[j] = kInf;
+    overflow[j] = false;
+  }
+  float bm_run = 0.0f;
+
+  for (int c0 = 0; c0 < (MULTI ? n : 1); c0 += CH) {
+    const int cn = min(CH, n - c0);
+    const int ntile = (cn + T - 1) / T;
+    bm_run = fmaxf(bm_run, stage_targets<THREADS, T>(tgt, red, pts, c0, n, ntile, tid));
+
+    // ---- pass A: filter scan, tile minima to smem, k+1 smallest group minima -----
+    {
+      int tpg = ntile / (2 * (k + 1));  // tiles per group; >= k+1 groups give a finite tau
+      if (tpg < 1) tpg = 1;
+      float S[Q][KL];
+      float gmin[Q];
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        gmin[j] = kInf;
+#pragma unroll
+        for (int s = 0; s < KL; s++) S[j][s] = kInf;
+      }
+      int left = tpg;
+      filter_scan<Q, T>(tgt, ntile, ax2, ay2, az2, [&](int tile, const float(&tm)[Q]) {
+#pragma unroll
+        for (int j = 0; j < Q; j++) gmin[j] = fminf(gmin[j], tm[j]);
+        if (--left == 0 || tile == ntile - 1) {
+          left = tpg;
+#pragma unroll
+          for (int j = 0; j < Q; j++) {
+            float v = gmin[j];
+            gmin[j] = kInf;
+#pragma unroll
+            for (int s = 0; s < KL; s++) {  // sorted insert by compare-exchange chain
+              const float lo = fminf(S[j][s], v);
+              v = fmaxf(S[j][s], v);
+              S[j][s] = lo;
+            }
+          }
+        }
+      });
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        float tk = kInf;
+#pragma unroll
+        for (int s = 0; s < KL; s++)
+          if (s == k) tk = S[j][s];  // (k+1)-th smallest group minimum
+        tau[j] = fminf(tau[j], tk);
+      }
+    }
+
+    // ---- pass B1: second scan, candidates (f <= tau + W) appended to per-query queues ----
+    // (the union of the tiles the 32 lanes of a warp need is essentially every tile, so the
+    // scan is a plain broadcast walk like pass A, not a per-lane walk over qualifying tiles)
+    float thr[Q];
+    int cnts[Q];
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+      // invalid / already overflowed slots collect nothing
+      thr[j] = (valid[j] && !overflow[j]) ? tau[j] + filter_window(qabs[j], bm_run) : -kInf;
+      cnts[j] = 0;
+    }
+    filter_collect<Q, T>(tgt, ntile, ax2, ay2, az2, thr, cnts, queue + tid, QT, THREADS, kKnnQueue);
+
+    // ---- pass B2, per query slot: drain the queue into the exact sorted list ------------
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+      if (!valid[j] || overflow[j]) continue;
+      const unsigned short* myq = queue + j * THREADS + tid;
+      const int cnt = cnts[j];
+      if (cnt > kKnnQueue) {  // dense neighbourhood / degenerate data: exact warp path below
+        overflow[j] = true;
+        continue;
+      }
+      // B2: drain the queue into the exact sorted list (all lanes step through their own
+      // queue together; the insert is order-independent)
+      float TLv[KL];
+      int TLi[KL];
+#pragma unroll
+      for (int s = 0; s < KL; s++) {
+        TLv[s] = MULTI ? PLv[MULTI ? j : 0][s] : kInf;
+        TLi[s] = MULTI ? PLi[MULTI ? j : 0][s] : -1;
+      }
+      for (int c = 0; c < cnt; c++) {
+        const int gl = myq[c * QT];  // chunk-local index
+        if (c0 + gl >= n) continue;  // padding can only get here when the threshold is not finite
+        const float* pu = reinterpret_cast<const float*>(tgt + 2 * (gl >> 1));
+        const int h = gl & 1;
+        const float d = sqdist<GA_MODE_CPU_EXACT>(pu[h], pu[2 + h], pu[4 + h], qx[j], qy[j], qz[j]);
+        if (d == d) list_insert<KL>(TLv, TLi, d, c0 + gl);  // NaN is never selected beyond position k
+      }
+      if (MULTI) {
+#pragma unroll
+        for (int s = 0; s < KL; s++) {
+          PLv[MULTI ? j : 0][s] = TLv[s];
+          PLi[MULTI ? j : 0][s] = TLi[s];
+        }
+        if (c0 + CH < n) continue;  // more chunks to merge
+      }
+      // ---- output / tie detection ----
+      const int qi = qtile * QT + j * THREADS + tid;
+      bool rp = replay[j];
+      float vk = kInf;
+#pragma unroll
+      for (int s = 0; s < KL; s++) {
+        if (s == k - 1) {
+          vk = TLv[s];
+          rp |= TLi[s] < 0;  // fewer than k finite distances
+        }
+        if (s + 1 < KL && s < k) rp |= (TLv[s] == TLv[s + 1]) && TLi[s + 1] >= 0;
+      }
+      if (need_idx && rp) {
+        const int slot = atomicAdd(flag_cnt, 1);
+        flag_q[slot] = j * THREADS + tid;
+        flag_vk[slot] = TLi[0] < 0 ? kInf : vk;
+        continue;
+      }
+      float* vo = a.val + ((size_t)batch * a.m + qi) * kout;
+      int* io = need_idx ? a.idx + ((size_t)batch * a.m + qi) * kout : nullptr;
+#pragma unroll
+      for (int s = 0; s < KL; s++) {
+        if (s >= a.skip && s < k) {
+          vo[s - a.skip] = a.do_sqrt ? __fsqrt_rn(TLv[s]) : TLv[s];
+          if (need_idx) io[s - a.skip] = TLi[s];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    if (valid[j] && overflow[j]) {
+      const int slot = atomicAdd(flag_cnt, 1);
+      flag_q[slot] = j * THREADS + tid;
+      flag_vk[slot] = kNaN;  // v_k unknown: the warp path computes it
+    }
+  }
+  __syncthreads();
+  // ---- flagged queries, one warp each: exact v_k if needed, then the replay ---------
+  const int nflag = *flag_cnt;
+  float* cv = reinterpret_cast<float*>(scratch + (size_t)warp * 3 * KL * 8);
+  int* ci = reinterpret_cast<int*>(cv + 3 * KL);
+  for (int f = warp; f < nflag; f += THREADS / 32) {
+    const int qi = qtile * QT + flag_q[f];
+    const float x = __ldg(qpts + (size_t)qi * 3), y = __ldg(qpts + (size_t)qi * 3 + 1),
+                z = __ldg(qpts + (size_t)qi * 3 + 2);
+    float vk = flag_vk[f];
+    if (vk != vk) vk = kth_smallest_warp(pts, n, x, y, z, k, lane);
+    selection_replay(pts, n, x, y, z, k, vk, cv, ci, lane);
+    write_replayed(cv, ci, k, a.skip, a.do_sqrt, a.val + ((size_t)batch * a.m + qi) * kout,
+                   need_idx ? a.idx + ((size_t)batch * a.m + qi) * kout : nullptr, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Generic k (k > 32): one warp per query, exact v_k then the replay.  O(k n) per
+// query; rare path (tf_grouping.py's own self-test uses k = 64).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) knn_generic_kernel(const KnnArgs a) {
+  extern __shared__ float4 smem_f4[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long q = (long long)blockIdx.x * 4 + warp;
+  if (q >= (long long)a.b * a.m) return;
+  const int batch = (int)(q / a.m), qi = (int)(q - (long long)batch * a.m);
+  const int n = a.n, k = a.k;
+  const float* pts = a.xyz1 + (size_t)batch * n * 3;
+  const float* qp = a.xyz2 + ((size_t)batch * a.m + qi) * 3;
+  const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+  const float vk = kth_smallest_warp(pts, n, qx, qy, qz, k, lane);
   float* cv = reinterpret_cast<float*>(smem_f4) + (size_t)warp * 6 * k;
   int* ci = reinterpret_cast<int*>(cv + 3 * k);
   const int kout = k - a.skip;
-  // replay writes k entries; with skip/do_sqrt the caller post-processes (not used with this kernel)
-  selection_replay(pts, n, qx, qy, qz, k, vk, cv, ci, a.val + ((size_t)batch * a.m + qi) * kout,
-                   a.idx + ((size_t)batch * a.m + qi) * kout, lane);
+  selection_replay(pts, n, qx, qy, qz, k, vk, cv, ci, lane);
+  write_replayed(cv, ci, k, a.skip, a.do_sqrt, a.val + ((size_t)batch * a.m + qi) * kout,
+                 a.idx ? a.idx + ((size_t)batch * a.m + qi) * kout : nullptr, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -435,18 +494,37 @@ static int launch_knn(const KnnArgs& a0, cudaStream_t st) {
   return GA_OK;
 }
 
+int g_knn_variant = 0;  // tuning hook
+
 static int knn_dispatch(const KnnArgs& a, cudaStream_t st) {
-  if (a.k + 1 <= 12) return launch_knn<KnnCfg<64, 2, 32, 2048, 12>>(a, st);
-  if (a.k + 1 <= 17) return launch_knn<KnnCfg<64, 2, 32, 2048, 17>>(a, st);
-  if (a.k + 1 <= 33) return launch_knn<KnnCfg<64, 1, 32, 2048, 33>>(a, st);
-  if (a.skip != 0 || a.do_sqrt != 0 || a.idx == nullptr) {
-    set_error("ga_knn_dists: k > 31 is not supported");
-    return GA_ERR_UNSUPPORTED;
+  const int kl = a.k + 1;
+  if (kl <= 33) {
+    if (a.n <= 2048) {  // single chunk: lists live only while a query slot is drained
+      if (kl <= 12) {
+        switch (g_knn_variant) {
+          case 1: return launch_knn<KnnCfg<64, 4, 32, 2048, 12, false>>(a, st);
+          case 2: return launch_knn<KnnCfg<128, 4, 32, 2048, 12, false>>(a, st);
+          case 3: return launch_knn<KnnCfg<256, 2, 32, 2048, 12, false>>(a, st);
+          case 4: return launch_knn<KnnCfg<64, 2, 32, 2048, 12, false>>(a, st);
+          case 5: return launch_knn<KnnCfg<128, 1, 32, 2048, 12, false>>(a, st);
+          default: return launch_knn<KnnCfg<128, 2, 32, 2048, 12, false>>(a, st);
+        }
+      }
+      if (kl <= 17) return launch_knn<KnnCfg<128, 2, 32, 2048, 17, false>>(a, st);
+      return launch_knn<KnnCfg<128, 1, 32, 2048, 33, false>>(a, st);
+    }
+    if (kl <= 12) return launch_knn<KnnCfg<128, 1, 32, 2048, 12, true>>(a, st);
+    if (kl <= 17) return launch_knn<KnnCfg<128, 1, 32, 2048, 17, true>>(a, st);
+    return launch_knn<KnnCfg<128, 1, 32, 2048, 33, true>>(a, st);
   }
   const long long queries = (long long)a.b * a.m;
   const size_t smem = (size_t)4 * 6 * a.k * 4;
   if (smem > 200 * 1024) {
     set_error("ga_knn: k = %d is too large", a.k);
+    return GA_ERR_UNSUPPORTED;
+  }
+  if ((queries + 3) / 4 > 0x7fffffffLL) {
+    set_error("ga_knn: problem too large for one launch");
     return GA_ERR_UNSUPPORTED;
   }
   GA_CUDA_TRY(cudaFuncSetAttribute(knn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

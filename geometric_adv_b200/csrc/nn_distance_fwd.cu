@@ -34,7 +34,7 @@ struct FwdCfg {
   static constexpr int kT = T;               // targets per filter tile
   static constexpr int kCH = CH;             // targets staged per chunk
   static constexpr size_t kSmem = (size_t)CH * 16 + (size_t)kPipeU * 32 + 32 * 4;
-  static_assert(CH % T == 0, "tile shapes");
+  static_assert(CH % T == 0 && (T & (T - 1)) == 0, "tile shapes");
 };
 
 struct FwdArgs {
@@ -55,8 +55,13 @@ template <int T, int MODE>
 __device__ __forceinline__ void refine_tile(const float4* __restrict__ tp, int g0, int nt, float ax2, float ay2,
                                             float az2, float qx, float qy, float qz, float thr, float& best,
                                             int& besti) {
+  // Lanes of a warp usually refine DIFFERENT tiles; tiles are a multiple of 1 KB apart, so
+  // walking them in step would put all 32 lanes on the same banks.  Each lane starts at its
+  // own pair instead (the update below is order-independent).
+  const int rot = threadIdx.x & 31;
 #pragma unroll 4
-  for (int pp = 0; pp < T / 2; pp++) {
+  for (int i = 0; i < T / 2; i++) {
+    const int pp = (i + rot) & (T / 2 - 1);
     const float4 u = tp[2 * pp];
     const float4 v = tp[2 * pp + 1];
     const float2 f = filter_pair(u, v, ax2, ay2, az2);
@@ -76,6 +81,45 @@ __device__ __forceinline__ void refine_tile(const float4* __restrict__ tp, int g
         besti = g + 1;
       }
     }
+  }
+}
+
+// Same walk as refine_tile, but only RECORDS which targets pass the filter (first two
+// indices + count, branch-free), so that all lanes stay in step; the exact evaluation
+// happens afterwards, once, for every lane together.
+template <int T>
+__device__ __forceinline__ void scan_tile_candidates(const float4* __restrict__ tp, int g0, int nt, float ax2,
+                                                     float ay2, float az2, float thr, int& cnt, int& ca,
+                                                     int& cb) {
+  const int rot = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < T / 2; i++) {
+    const int pp = (i + rot) & (T / 2 - 1);
+    const float4 u = tp[2 * pp];
+    const float4 v = tp[2 * pp + 1];
+    const float2 f = filter_pair(u, v, ax2, ay2, az2);
+    const int g = g0 + 2 * pp;
+    const bool p0 = !(f.x > thr) && g < nt;  // NaN filter value / threshold counts as a candidate
+    const bool p1 = !(f.y > thr) && g + 1 < nt;
+    cb = (p0 && cnt == 1) ? g : cb;
+    ca = (p0 && cnt == 0) ? g : ca;
+    cnt += p0 ? 1 : 0;
+    cb = (p1 && cnt == 1) ? g + 1 : cb;
+    ca = (p1 && cnt == 0) ? g + 1 : ca;
+    cnt += p1 ? 1 : 0;
+  }
+}
+
+// Reference arithmetic for one staged target (index g in the chunk starting at c0).
+template <int MODE>
+__device__ __forceinline__ void eval_candidate(const float4* __restrict__ tgt, int c0, int g, float qx, float qy,
+                                               float qz, float& best, int& besti) {
+  const int p = (g - c0) >> 1, h = (g - c0) & 1;
+  const float* pu = reinterpret_cast<const float*>(tgt + 2 * p);
+  const float d = sqdist<MODE>(pu[h], pu[2 + h], pu[4 + h], qx, qy, qz);
+  if (d < best || (d == best && g < besti)) {
+    best = d;
+    besti = g;
   }
 }
 
@@ -159,18 +203,37 @@ __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_kernel(const FwdArgs a) 
       if (!valid[j]) continue;
       m1g[j] = fminf(m1g[j], c1[j]);
       const float thr = m1g[j] + filter_window(qabs[j], bm_run);
-      if (!(c3[j] > thr)) {
-        // three or more tiles within the window (or non-finite data): scan the whole chunk
+      const bool all_tiles = !(c3[j] > thr);  // three or more tiles in the window, or non-finite data
+      const bool t1 = !(c1[j] > thr), t2 = !(c2[j] > thr);
+      int cnt = 0, ca = 0, cb = 0;
+      if (all_tiles) {
         for (int tile = 0; tile < ntile; tile++)
-          refine_tile<T, MODE>(tgt + (size_t)tile * T, c0 + tile * T, nt, ax2[j], ay2[j], az2[j], qx[j], qy[j],
-                               qz[j], thr, best[j], besti[j]);
+          scan_tile_candidates<T>(tgt + (size_t)tile * T, c0 + tile * T, nt, ax2[j], ay2[j], az2[j], thr, cnt, ca,
+                                  cb);
       } else {
-        if (!(c1[j] > thr))
-          refine_tile<T, MODE>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, ax2[j], ay2[j], az2[j], qx[j], qy[j],
-                               qz[j], thr, best[j], besti[j]);
-        if (!(c2[j] > thr))
-          refine_tile<T, MODE>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, ax2[j], ay2[j], az2[j], qx[j], qy[j],
-                               qz[j], thr, best[j], besti[j]);
+        if (t1)
+          scan_tile_candidates<T>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, ax2[j], ay2[j], az2[j], thr, cnt,
+                                  ca, cb);
+        if (t2)
+          scan_tile_candidates<T>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, ax2[j], ay2[j], az2[j], thr, cnt,
+                                  ca, cb);
+      }
+      if (cnt <= 2) {  // the usual case: one or two survivors, evaluated by all lanes in step
+        if (cnt >= 1) eval_candidate<MODE>(tgt, c0, ca, qx[j], qy[j], qz[j], best[j], besti[j]);
+        if (cnt >= 2) eval_candidate<MODE>(tgt, c0, cb, qx[j], qy[j], qz[j], best[j], besti[j]);
+      } else {         // many survivors (ties, degenerate or non-finite data): walk again, evaluating inline
+        if (all_tiles) {
+          for (int tile = 0; tile < ntile; tile++)
+            refine_tile<T, MODE>(tgt + (size_t)tile * T, c0 + tile * T, nt, ax2[j], ay2[j], az2[j], qx[j], qy[j],
+                                 qz[j], thr, best[j], besti[j]);
+        } else {
+          if (t1)
+            refine_tile<T, MODE>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, ax2[j], ay2[j], az2[j], qx[j],
+                                 qy[j], qz[j], thr, best[j], besti[j]);
+          if (t2)
+            refine_tile<T, MODE>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, ax2[j], ay2[j], az2[j], qx[j],
+                                 qy[j], qz[j], thr, best[j], besti[j]);
+        }
       }
     }
   }
@@ -246,15 +309,17 @@ extern "C" int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const 
     a.tiles2 = (m + Cfg::kQT - 1) / Cfg::kQT;                                                    \
     return launch_fwd<Cfg>(a, mode, st);                                                         \
   }
-    GA_FWD_CASE(1, 128, 2, 64, 2048)
+    GA_FWD_CASE(1, 128, 4, 32, 2048)
     GA_FWD_CASE(2, 64, 4, 64, 2048)
     GA_FWD_CASE(3, 64, 2, 32, 2048)
-    GA_FWD_CASE(4, 64, 2, 64, 1024)
-    GA_FWD_CASE(5, 128, 1, 64, 2048)
-    GA_FWD_CASE(6, 64, 2, 128, 2048)
-    GA_FWD_CASE(7, 128, 4, 64, 2048)
+    GA_FWD_CASE(4, 128, 2, 32, 2048)
+    GA_FWD_CASE(5, 64, 8, 32, 2048)
+    GA_FWD_CASE(6, 32, 8, 32, 2048)
+    GA_FWD_CASE(7, 64, 4, 16, 2048)
+    GA_FWD_CASE(8, 32, 4, 32, 2048)
+    GA_FWD_CASE(9, 64, 4, 32, 1024)
     default:
-    GA_FWD_CASE(0, 64, 2, 64, 2048)
+    GA_FWD_CASE(0, 64, 4, 32, 2048)
 #undef GA_FWD_CASE
   }
 }

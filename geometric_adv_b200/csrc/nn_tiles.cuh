@@ -24,26 +24,38 @@ __device__ __forceinline__ float stage_targets(float4* __restrict__ tgt, float* 
   const float kInf = __int_as_float(0x7f800000);
   __syncthreads();  // previous contents fully consumed
   float lmax = 0.0f;
-  for (int p = tid; p < ntile * (T / 2); p += THREADS) {
-    const int g = c0 + 2 * p;
-    float x0 = 0.f, y0 = 0.f, z0 = 0.f, n0 = kInf;
-    float x1 = 0.f, y1 = 0.f, z1 = 0.f, n1 = kInf;
-    if (g < nt) {
-      x0 = __ldg(tpts + (size_t)g * 3);
-      y0 = __ldg(tpts + (size_t)g * 3 + 1);
-      z0 = __ldg(tpts + (size_t)g * 3 + 2);
-      n0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
-      lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(x0), fabsf(y0)), fabsf(z0)));
+  // SB pairs per thread per round: all 6*SB loads are issued before any is used
+  constexpr int SB = 4;
+  const int npair = ntile * (T / 2);
+  for (int p0 = tid; p0 < npair; p0 += THREADS * SB) {
+    float c[SB][6];
+#pragma unroll
+    for (int s = 0; s < SB; s++) {
+      const int p = p0 + s * THREADS;
+      const long long g = (long long)c0 + 2 * p;
+#pragma unroll
+      for (int e = 0; e < 6; e++) {
+        const bool ok = p < npair && g + (e >= 3) < nt;
+        c[s][e] = ok ? __ldg(tpts + g * 3 + e) : 0.0f;
+      }
     }
-    if (g + 1 < nt) {
-      x1 = __ldg(tpts + (size_t)g * 3 + 3);
-      y1 = __ldg(tpts + (size_t)g * 3 + 4);
-      z1 = __ldg(tpts + (size_t)g * 3 + 5);
-      n1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
-      lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(x1), fabsf(y1)), fabsf(z1)));
+#pragma unroll
+    for (int s = 0; s < SB; s++) {
+      const int p = p0 + s * THREADS;
+      if (p >= npair) break;
+      const int g = c0 + 2 * p;
+      float n0 = kInf, n1 = kInf;
+      if (g < nt) {
+        n0 = fmaf(c[s][2], c[s][2], fmaf(c[s][1], c[s][1], c[s][0] * c[s][0]));
+        lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(c[s][0]), fabsf(c[s][1])), fabsf(c[s][2])));
+      }
+      if (g + 1 < nt) {
+        n1 = fmaf(c[s][5], c[s][5], fmaf(c[s][4], c[s][4], c[s][3] * c[s][3]));
+        lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(c[s][3]), fabsf(c[s][4])), fabsf(c[s][5])));
+      }
+      tgt[2 * p] = make_float4(c[s][0], c[s][3], c[s][1], c[s][4]);
+      tgt[2 * p + 1] = make_float4(c[s][2], c[s][5], n0, n1);
     }
-    tgt[2 * p] = make_float4(x0, x1, y0, y1);
-    tgt[2 * p + 1] = make_float4(z0, z1, n0, n1);
   }
   lmax = warp_max(lmax);
   if ((tid & 31) == 0) red[tid >> 5] = lmax;
@@ -52,6 +64,14 @@ __device__ __forceinline__ float stage_targets(float4* __restrict__ tgt, float* 
 #pragma unroll
   for (int w = 0; w < THREADS / 32; w++) bm = fmaxf(bm, red[w]);
   return bm;
+}
+
+// Filter values of one staged pair for one query.
+__device__ __forceinline__ float2 filter_pair(const float4 u, const float4 v, float ax2, float ay2, float az2) {
+  float2 f = ffma2(make_float2(az2, az2), make_float2(v.x, v.y), make_float2(v.z, v.w));
+  f = ffma2(make_float2(ay2, ay2), make_float2(u.z, u.w), f);
+  f = ffma2(make_float2(ax2, ax2), make_float2(u.x, u.y), f);
+  return f;
 }
 
 // Filter scan over `ntile` tiles of T targets for Q queries per thread.  After
@@ -95,12 +115,48 @@ __device__ __forceinline__ void filter_scan(const float4* __restrict__ tgt, int 
   }
 }
 
-// Filter values of one staged pair for one query.
-__device__ __forceinline__ float2 filter_pair(const float4 u, const float4 v, float ax2, float ay2, float az2) {
-  float2 f = ffma2(make_float2(az2, az2), make_float2(v.x, v.y), make_float2(v.z, v.w));
-  f = ffma2(make_float2(ay2, ay2), make_float2(u.z, u.w), f);
-  f = ffma2(make_float2(ax2, ax2), make_float2(u.x, u.y), f);
-  return f;
+// Second scan for kNN: same pipelined walk as filter_scan, but every target whose
+// filter value is <= thr[j] is appended (chunk-local index, 16 bit) to query j's
+// queue.  Appends are predicated, not branched, so the warp stays in step; row
+// `cap` of the queue is a scratch row that absorbs writes after an overflow.
+template <int Q, int T>
+__device__ __forceinline__ void filter_collect(const float4* __restrict__ tgt, int ntile, const float (&ax2)[Q],
+                                               const float (&ay2)[Q], const float (&az2)[Q],
+                                               const float (&thr)[Q], int (&cnt)[Q],
+                                               unsigned short* __restrict__ queue, int qstride, int jstride,
+                                               int cap) {
+  constexpr int U = kPipeU;
+  constexpr int NB = (T / 2) / U;
+  float4 buf[2][2 * U];
+#pragma unroll
+  for (int e = 0; e < 2 * U; e++) buf[0][e] = tgt[e];
+#pragma unroll 1
+  for (int tile = 0; tile < ntile; tile++) {
+    const float4* tp = tgt + (size_t)tile * T;
+#pragma unroll
+    for (int blk = 0; blk < NB; blk++) {
+#pragma unroll
+      for (int e = 0; e < 2 * U; e++) buf[(blk + 1) & 1][e] = tp[(blk + 1) * 2 * U + e];
+#pragma unroll
+      for (int pp = 0; pp < U; pp++) {
+        const float4 u = buf[blk & 1][2 * pp];
+        const float4 v = buf[blk & 1][2 * pp + 1];
+        const int g = tile * T + (blk * U + pp) * 2;
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+          const float2 f = filter_pair(u, v, ax2[j], ay2[j], az2[j]);
+          if (!(f.x > thr[j])) {  // NaN filter value / threshold counts as a candidate
+            queue[min(cnt[j], cap) * qstride + j * jstride] = (unsigned short)g;
+            cnt[j]++;
+          }
+          if (!(f.y > thr[j])) {
+            queue[min(cnt[j], cap) * qstride + j * jstride] = (unsigned short)(g + 1);
+            cnt[j]++;
+          }
+        }
+      }
+    }
+  }
 }
 
 // Window of the filter (see nn_distance_fwd.cu): W = 128u (A+Bm)^2 + denormal slack.

@@ -66,7 +66,7 @@ for (b, n, m) in [(50, 2048, 2048), (10, 2048, 2048), (1, 2048, 2048), (512, 204
     pairs = float(b) * n * m
     key = "fwd_b%d" % b
     out[key] = {}
-    for v in range(0, 8):
+    for v in range(0, 10):
         lib.ga_set_tuning(0, v)
         r = timeit(lambda: lib.ga_nn_distance_fwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()),
                                                   p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()), 0, p(st)))
@@ -98,10 +98,13 @@ for (b, n, m) in [(50, 2048, 2048), (10, 2048, 2048), (1, 2048, 2048), (512, 204
 for (b, n, k) in [(100, 2048, 10), (500, 2048, 10)]:
     pc = clouds(b, n, 4)
     o = torch.empty(b, n, k, device=dev)
-    r = timeit(lambda: lib.ga_knn_dists(b, n, k, p(pc.data_ptr()), p(o.data_ptr()), p(st)), reps=10)
-    r["pairs_per_s"] = float(b) * n * n / (r["min_ms"] * 1e-3)
-    out["knn_dists_b%d" % b] = r
-    print("knn_dists", b, r, flush=True)
+    for v in range(6):
+        lib.ga_set_tuning(1, v)
+        r = timeit(lambda: lib.ga_knn_dists(b, n, k, p(pc.data_ptr()), p(o.data_ptr()), p(st)), reps=10)
+        r["pairs_per_s"] = float(b) * n * n / (r["min_ms"] * 1e-3)
+        out["knn_dists_b%d_v%d" % (b, v)] = r
+        print("knn_dists", b, "variant", v, r, flush=True)
+    lib.ga_set_tuning(1, 0)
     val = torch.empty(b, n, k + 1, device=dev); idx = torch.empty(b, n, k + 1, dtype=torch.int32, device=dev)
     r = timeit(lambda: lib.ga_knn(b, n, n, k + 1, p(pc.data_ptr()), p(pc.data_ptr()), p(val.data_ptr()),
                                   p(idx.data_ptr()), p(st)), reps=10)
