@@ -1,9 +1,180 @@
-// All-pairs Chamfer matrix (attacker/prepare_indices_for_attack.py:104-139).
-#include "nn_tiles.cuh"
+// All-pairs Chamfer matrix: the driver loop of
+// attacker/prepare_indices_for_attack.py:104-139 as one kernel.
+//
+// Reference: tiles two (all,100,2048,3) host arrays, feeds 100 cloud pairs per
+// sess.run through nn_distance, reduces mean(d_s_t,1)+mean(d_t_s,1), and repeats
+// 44 x 438 times.  Here the directed term
+//     D[a -> b] = mean over points p of cloud a of min_q |p - q|^2, q in cloud b
+// is computed by CTAs that stage cloud b ONCE in shared memory and stream a block
+// of source clouds through it (all clouds stay L2-resident: 2,000 x 24 KB = 49 MB);
+// no per-point dist/idx array is ever written.  CD[i,j] = D[j->i] + D[i->j].
+// Same filter-and-refine search as nn_distance_fwd.cu, so every per-point distance
+// is bit-identical to the reference arithmetic; the per-cloud mean uses a fixed
+// summation tree (the reference's reduce_mean order is unpinned: tolerance 1e-6).
+#include "nn_search.cuh"
 
-extern "C" int ga_chamfer_all_pairs(int s, int n, const float* clouds, int row0, int rows, float* out, int mode,
-                                    ga_stream_t stream) {
-  (void)s; (void)n; (void)clouds; (void)row0; (void)rows; (void)out; (void)mode; (void)stream;
-  ga::set_error("ga_chamfer_all_pairs: not built yet");
-  return GA_ERR_UNSUPPORTED;
+namespace ga {
+
+struct PairArgs {
+  int s, n;             // clouds, points per cloud
+  const float* clouds;  // (s,n,3)
+  int a0, na;           // source clouds [a0, a0+na)
+  int b0, nb;           // target clouds [b0, b0+nb)
+  float* out;           // out[(a-a0)*stride_a + (b-b0)*stride_b] = D[a -> b]
+  long long stride_a, stride_b;
+  int ablk;             // source clouds per CTA
+  int accumulate;       // add to out instead of overwriting (second direction of a CD row block)
+};
+
+using PairCfg = FwdCfg<128, 4, 32, 2048>;
+
+template <int MODE>
+__global__ void __launch_bounds__(PairCfg::kThreads) all_pairs_directed_kernel(const PairArgs a) {
+  using Cfg = PairCfg;
+  constexpr int THREADS = Cfg::kThreads, Q = Cfg::kQ, QT = Cfg::kQT, T = Cfg::kT, CH = Cfg::kCH;
+  extern __shared__ float4 smem_f4[];
+  float4* tgt = smem_f4;
+  float* red = reinterpret_cast<float*>(smem_f4 + CH + 2 * kPipeU);  // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n;
+  const int nblk = (a.na + a.ablk - 1) / a.ablk;
+  const int bj = blockIdx.x / nblk;            // target cloud (slow index: neighbours share sources in L2)
+  const int ab = blockIdx.x - bj * nblk;
+  const int b = a.b0 + bj;
+  const float* tpts = a.clouds + (size_t)b * n * 3;
+  const int ntile = (n + T - 1) / T;
+  const float bm = stage_targets<THREADS, T>(tgt, red, tpts, 0, n, ntile, tid);
+  const int qtiles = (n + QT - 1) / QT;
+  const int a_end = min(a.na, (ab + 1) * a.ablk);
+  for (int ai = ab * a.ablk; ai < a_end; ai++) {
+    const float* qpts = a.clouds + (size_t)(a.a0 + ai) * n * 3;
+    float part = 0.0f;  // this thread's distances, summed in (tile, slot) order
+    for (int qt = 0; qt < qtiles; qt++) {
+      QueryState<Q> s;
+      load_queries<Cfg, MODE>(s, qpts, n, qt, tpts, tid);
+      search_chunk<Cfg, MODE>(s, tgt, 0, n, ntile, bm);
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        if (!s.valid[j]) continue;
+        float d;
+        int i;
+        finish_query<Q>(s, j, d, i);
+        part += d;
+      }
+    }
+    // fixed tree: lanes by xor-shuffle, then warps in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();  // red[] free (staging / previous cloud done)
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < THREADS / 32; w++) t += red[w];
+      float* o = a.out + (long long)ai * a.stride_a + (long long)bj * a.stride_b;
+      const float v = t / (float)n;
+      *o = a.accumulate ? *o + v : v;
+    }
+  }
 }
+
+static int launch_directed(const PairArgs& a, int mode, cudaStream_t st) {
+  if (a.na <= 0 || a.nb <= 0) return GA_OK;
+  const long long ctas = (long long)a.nb * ((a.na + a.ablk - 1) / a.ablk);
+  if (ctas > 0x7fffffffLL) {
+    set_error("ga_chamfer_all_pairs: problem too large for one launch");
+    return GA_ERR_UNSUPPORTED;
+  }
+  auto k = mode == GA_MODE_CPU_EXACT ? all_pairs_directed_kernel<GA_MODE_CPU_EXACT>
+                                     : all_pairs_directed_kernel<GA_MODE_GPU_REF>;
+  GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::kSmem));
+  k<<<(unsigned)ctas, PairCfg::kThreads, PairCfg::kSmem, st>>>(a);
+  GA_LAUNCH_CHECK("all_pairs_directed_kernel");
+  return GA_OK;
+}
+
+static int choose_ablk(int na, int nb) {
+  // enough CTAs to fill the machine several times over, as much reuse of the staged cloud as that allows
+  const long long want = (long long)sm_count() * 16;
+  int ablk = 16;
+  while (ablk > 1 && (long long)nb * ((na + ablk - 1) / ablk) < want) ablk >>= 1;
+  return ablk;
+}
+
+static int check_args(const char* who, int s, int n, const void* clouds, int row0, int rows, const void* out,
+                      int mode) {
+  if (s < 0 || n < 0 || row0 < 0 || rows < 0 || row0 + rows > s) {
+    set_error("%s: bad sizes (s=%d n=%d row0=%d rows=%d)", who, s, n, row0, rows);
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  if (mode != GA_MODE_CPU_EXACT && mode != GA_MODE_GPU_REF) {
+    set_error("%s: unknown mode %d", who, mode);
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  if (rows > 0 && s > 0 && (clouds == nullptr || out == nullptr)) {
+    set_error("%s: null pointer", who);
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  if (n > PairCfg::kCH) {
+    set_error("%s: clouds larger than %d points are not supported by the all-pairs kernel (n=%d); "
+              "use ga_nn_distance_fwd on batches", who, PairCfg::kCH, n);
+    return GA_ERR_UNSUPPORTED;
+  }
+  return GA_OK;
+}
+
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" {
+
+int ga_chamfer_all_pairs_directed(int s, int n, const float* clouds, int row0, int rows, float* out, int mode,
+                                  ga_stream_t stream) {
+  int rc = check_args("ga_chamfer_all_pairs_directed", s, n, clouds, row0, rows, out, mode);
+  if (rc != GA_OK) return rc;
+  if (rows == 0 || s == 0) return GA_OK;
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {  // mean over nothing: the reference would produce NaN (0/0)
+    GA_CUDA_TRY(cudaMemsetAsync(out, 0xff, sizeof(float) * (size_t)rows * s, st));
+    return GA_OK;
+  }
+  PairArgs a;
+  a.s = s; a.n = n; a.clouds = clouds;
+  a.a0 = row0; a.na = rows; a.b0 = 0; a.nb = s;
+  a.out = out; a.stride_a = s; a.stride_b = 1;
+  a.ablk = choose_ablk(rows, s);
+  a.accumulate = 0;
+  return launch_directed(a, mode, st);
+}
+
+int ga_chamfer_all_pairs(int s, int n, const float* clouds, int row0, int rows, float* out, int mode,
+                         ga_stream_t stream) {
+  int rc = check_args("ga_chamfer_all_pairs", s, n, clouds, row0, rows, out, mode);
+  if (rc != GA_OK) return rc;
+  if (rows == 0 || s == 0) return GA_OK;
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    GA_CUDA_TRY(cudaMemsetAsync(out, 0xff, sizeof(float) * (size_t)rows * s, st));
+    return GA_OK;
+  }
+  // out[r, j] = CD(source = clouds[j], target = clouds[row0+r]) = D[j -> i] + D[i -> j], i = row0 + r
+  PairArgs a;
+  a.s = s; a.n = n; a.clouds = clouds; a.out = out;
+  // first D[j -> i]: sources j = all clouds, targets i = the row block
+  a.a0 = 0; a.na = s; a.b0 = row0; a.nb = rows;
+  a.stride_a = 1; a.stride_b = s;
+  a.ablk = choose_ablk(s, rows);
+  a.accumulate = 0;
+  rc = launch_directed(a, mode, st);
+  if (rc != GA_OK) return rc;
+  // then += D[i -> j]
+  a.a0 = row0; a.na = rows; a.b0 = 0; a.nb = s;
+  a.stride_a = s; a.stride_b = 1;
+  a.ablk = choose_ablk(rows, s);
+  a.accumulate = 1;
+  return launch_directed(a, mode, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// Per-thread nearest-neighbour search over a target cloud staged in shared memory:
+// the filter-and-refine core shared by nn_distance_fwd.cu (writes dist/idx per query)
+// and all_pairs.cu (sums dist per cloud pair).  See nn_distance_fwd.cu for the method
+// and the rounding bound.
+#pragma once
+#include "nn_tiles.cuh"
+
+namespace ga {
+
+template <int THREADS, int Q, int T, int CH>
+struct FwdCfg {
+  static constexpr int kThreads = THREADS;
+  static constexpr int kQ = Q;               // queries per thread
+  static constexpr int kQT = THREADS * Q;    // queries per CTA
+  static constexpr int kT = T;               // targets per filter tile
+  static constexpr int kCH = CH;             // targets staged per chunk
+  static constexpr size_t kSmem = (size_t)CH * 16 + (size_t)kPipeU * 32 + 32 * 4;
+  static_assert(CH % T == 0 && (T & (T - 1)) == 0, "tile shapes");
+};
+
+// Re-evaluate one tile for one query: filter again per target, and evaluate the
+// survivors in the reference arithmetic.  Lexicographic (d, index) update so the
+// order in which tiles are refined does not matter.
+template <int T, int MODE>
+__device__ __forceinline__ void refine_tile(const float4* __restrict__ tp, int g0, int nt, float ax2, float ay2,
+                                            float az2, float qx, float qy, float qz, float thr, float& best,
+                                            int& besti) {
+  // Lanes of a warp usually refine DIFFERENT tiles; tiles are a multiple of 1 KB apart, so
+  // walking them in step would put all 32 lanes on the same banks.  Each lane starts at its
+  // own pair instead (the update below is order-independent).
+  const int rot = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < T / 2; i++) {
+    const int pp = (i + rot) & (T / 2 - 1);
+    const float4 u = tp[2 * pp];
+    const float4 v = tp[2 * pp + 1];
+    const float2 f = filter_pair(u, v, ax2, ay2, az2);
+    if (fminf(f.x, f.y) > thr) continue;  // NaN threshold falls through
+    const int g = g0 + 2 * pp;
+    if (!(f.x > thr) && g < nt) {
+      const float d = sqdist<MODE>(u.x, u.z, v.x, qx, qy, qz);
+      if (d < best || (d == best && g < besti)) {
+        best = d;
+        besti = g;
+      }
+    }
+    if (!(f.y > thr) && g + 1 < nt) {
+      const float d = sqdist<MODE>(u.y, u.w, v.y, qx, qy, qz);
+      if (d < best || (d == best && g + 1 < besti)) {
+        best = d;
+        besti = g + 1;
+      }
+    }
+  }
+}
+
+// Same walk as refine_tile, but only RECORDS which targets pass the filter (first two
+// indices + count, branch-free), so that all lanes stay in step; the exact evaluation
+// happens afterwards, once, for every lane together.
+template <int T>
+__device__ __forceinline__ void scan_tile_candidates(const float4* __restrict__ tp, int g0, int nt, float ax2,
+                                                     float ay2, float az2, float thr, int& cnt, int& ca,
+                                                     int& cb) {
+  const int rot = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < T / 2; i++) {
+    const int pp = (i + rot) & (T / 2 - 1);
+    const float4 u = tp[2 * pp];
+    const float4 v = tp[2 * pp + 1];
+    const float2 f = filter_pair(u, v, ax2, ay2, az2);
+    const int g = g0 + 2 * pp;
+    const bool p0 = !(f.x > thr) && g < nt;  // NaN filter value / threshold counts as a candidate
+    const bool p1 = !(f.y > thr) && g + 1 < nt;
+    cb = (p0 && cnt == 1) ? g : cb;
+    ca = (p0 && cnt == 0) ? g : ca;
+    cnt += p0 ? 1 : 0;
+    cb = (p1 && cnt == 1) ? g + 1 : cb;
+    ca = (p1 && cnt == 0) ? g + 1 : ca;
+    cnt += p1 ? 1 : 0;
+  }
+}
+
+// Reference arithmetic for one staged target (index g in the chunk starting at c0).
+template <int MODE>
+__device__ __forceinline__ void eval_candidate(const float4* __restrict__ tgt, int c0, int g, float qx, float qy,
+                                               float qz, float& best, int& besti) {
+  const int p = (g - c0) >> 1, h = (g - c0) & 1;
+  const float* pu = reinterpret_cast<const float*>(tgt + 2 * p);
+  const float d = sqdist<MODE>(pu[h], pu[2 + h], pu[4 + h], qx, qy, qz);
+  if (d < best || (d == best && g < besti)) {
+    best = d;
+    besti = g;
+  }
+}
+
+// Q queries per thread: coordinates, filter coefficients, running results.
+template <int Q>
+struct QueryState {
+  float qx[Q], qy[Q], qz[Q], qabs[Q], ax2[Q], ay2[Q], az2[Q];
+  float d0[Q];     // reference arithmetic to target 0 ("k==0 ||" seeds best with d(0))
+  float best[Q];   // exact running minimum
+  int besti[Q];
+  float m1g[Q];    // running minimum of the filter over all chunks seen
+  bool valid[Q];
+};
+
+// Load the Q queries of this thread (query tile `qtile` of a cloud with nq points).
+template <class Cfg, int MODE>
+__device__ __forceinline__ void load_queries(QueryState<Cfg::kQ>& s, const float* __restrict__ qpts, int nq,
+                                             int qtile, const float* __restrict__ tpts, int tid) {
+  constexpr int Q = Cfg::kQ, QT = Cfg::kQT, THREADS = Cfg::kThreads;
+  const float kInf = __int_as_float(0x7f800000);
+  const float t0x = __ldg(tpts), t0y = __ldg(tpts + 1), t0z = __ldg(tpts + 2);
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    const int qi = qtile * QT + j * THREADS + tid;
+    s.valid[j] = qi < nq;
+    const int qs = s.valid[j] ? qi : 0;
+    s.qx[j] = __ldg(qpts + (size_t)qs * 3);
+    s.qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
+    s.qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
+    s.qabs[j] = query_abs(s.qx[j], s.qy[j], s.qz[j]);
+    s.ax2[j] = -2.0f * s.qx[j];
+    s.ay2[j] = -2.0f * s.qy[j];
+    s.az2[j] = -2.0f * s.qz[j];
+    s.d0[j] = sqdist<MODE>(t0x, t0y, t0z, s.qx[j], s.qy[j], s.qz[j]);
+    s.best[j] = kInf;
+    s.besti[j] = 0;
+    s.m1g[j] = kInf;
+  }
+}
+
+// Search one staged chunk (targets [c0, c0 + ntile*T) of a cloud with nt points).
+// bm_run: max |coordinate| over all targets staged so far (including this chunk).
+template <class Cfg, int MODE>
+__device__ __forceinline__ void search_chunk(QueryState<Cfg::kQ>& s, const float4* __restrict__ tgt, int c0, int nt,
+                                             int ntile, float bm_run) {
+  constexpr int Q = Cfg::kQ, T = Cfg::kT;
+  const float kInf = __int_as_float(0x7f800000);
+  // ---- phase 1: filter scan; three smallest tile minima per query ----------
+  float c1[Q], c2[Q], c3[Q];
+  int i1[Q], i2[Q];
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    c1[j] = c2[j] = c3[j] = kInf;
+    i1[j] = i2[j] = 0;
+  }
+  filter_scan<Q, T>(tgt, ntile, s.ax2, s.ay2, s.az2, [&](int tile, const float(&tm)[Q]) {
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+      const bool lt1 = tm[j] < c1[j], lt2 = tm[j] < c2[j];
+      c3[j] = fminf(c3[j], fmaxf(c2[j], tm[j]));
+      i2[j] = lt1 ? i1[j] : (lt2 ? tile : i2[j]);
+      c2[j] = fminf(c2[j], fmaxf(c1[j], tm[j]));
+      i1[j] = lt1 ? tile : i1[j];
+      c1[j] = fminf(c1[j], tm[j]);
+    }
+  });
+
+  // ---- phase 2: refine the qualifying tiles in the reference arithmetic -----
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    if (!s.valid[j]) continue;
+    s.m1g[j] = fminf(s.m1g[j], c1[j]);
+    const float thr = s.m1g[j] + filter_window(s.qabs[j], bm_run);
+    const bool all_tiles = !(c3[j] > thr);  // three or more tiles in the window, or non-finite data
+    const bool t1 = !(c1[j] > thr), t2 = !(c2[j] > thr);
+    int cnt = 0, ca = 0, cb = 0;
+    if (all_tiles) {
+      for (int tile = 0; tile < ntile; tile++)
+        scan_tile_candidates<T>(tgt + (size_t)tile * T, c0 + tile * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr, cnt,
+                                ca, cb);
+    } else {
+      if (t1)
+        scan_tile_candidates<T>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
+                                cnt, ca, cb);
+      if (t2)
+        scan_tile_candidates<T>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
+                                cnt, ca, cb);
+    }
+    if (cnt <= 2) {  // the usual case: one or two survivors, evaluated by all lanes in step
+      if (cnt >= 1) eval_candidate<MODE>(tgt, c0, ca, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+      if (cnt >= 2) eval_candidate<MODE>(tgt, c0, cb, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+    } else {         // many survivors (ties, degenerate or non-finite data): walk again, evaluating inline
+      if (all_tiles) {
+        for (int tile = 0; tile < ntile; tile++)
+          refine_tile<T, MODE>(tgt + (size_t)tile * T, c0 + tile * T, nt, s.ax2[j], s.ay2[j], s.az2[j], s.qx[j],
+                               s.qy[j], s.qz[j], thr, s.best[j], s.besti[j]);
+      } else {
+        if (t1)
+          refine_tile<T, MODE>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], s.qx[j],
+                               s.qy[j], s.qz[j], thr, s.best[j], s.besti[j]);
+        if (t2)
+          refine_tile<T, MODE>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], s.qx[j],
+                               s.qy[j], s.qz[j], thr, s.best[j], s.besti[j]);
+      }
+    }
+  }
+}
+
+// Final (dist, idx) of query slot j with the reference's NaN-seed rule.
+template <int Q>
+__device__ __forceinline__ void finish_query(const QueryState<Q>& s, int j, float& dist, int& idx) {
+  const bool seed_nan = s.d0[j] != s.d0[j];  // reference: best = d(0) = NaN is never replaced
+  dist = seed_nan ? s.d0[j] : s.best[j];
+  idx = seed_nan ? 0 : s.besti[j];
+}
+
+}  // namespace ga

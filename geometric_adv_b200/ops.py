@@ -217,10 +217,11 @@ def chamfer_per_cloud(dist1, dist2):
     return out
 
 
-def chamfer_all_pairs(clouds, row0=0, rows=None, mode=None):
+def chamfer_all_pairs(clouds, row0=0, rows=None, mode=None, directed=False):
     """Rows [row0, row0+rows) of the all-pairs Chamfer matrix of
     attacker/prepare_indices_for_attack.py:104-139: out[r, j] = CD(source=clouds[j],
-    target=clouds[row0+r])."""
+    target=clouds[row0+r]).  directed=True returns only D[row0+r -> j] (mean over the points
+    of clouds[row0+r] of the squared distance to their nearest point of clouds[j]); CD = D + D^T."""
     lib = _lib.load()
     clouds = _prep(clouds, torch.float32, "clouds")
     if clouds.dim() != 3 or clouds.shape[2] != 3:
@@ -233,9 +234,9 @@ def chamfer_all_pairs(clouds, row0=0, rows=None, mode=None):
         raise ValueError("row block [%d, %d) outside 0..%d" % (row0, row0 + rows, s))
     out = torch.empty((rows, s), dtype=torch.float32, device=clouds.device)
     mode = _default_mode if mode is None else mode
+    fn = lib.ga_chamfer_all_pairs_directed if directed else lib.ga_chamfer_all_pairs
     with _Guard(clouds.device):
-        _lib.check(lib.ga_chamfer_all_pairs(s, n, clouds.data_ptr(), row0, rows, out.data_ptr(), mode,
-                                            _stream(clouds)))
+        _lib.check(fn(s, n, clouds.data_ptr(), row0, rows, out.data_ptr(), mode, _stream(clouds)))
     return out
 
 

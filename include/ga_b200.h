@@ -108,6 +108,12 @@ int ga_chamfer_per_cloud(int b, int n, int m, const float* dist1, const float* d
  * :139,151.  Row blocks are the multi-GPU shard unit. */
 int ga_chamfer_all_pairs(int s, int n, const float* clouds, int row0, int rows, float* out, int mode,
                          ga_stream_t stream);
+/* One direction only: out[r, j] = mean over the points p of clouds[row0 + r] of
+ * min_q |p - q|^2, q in clouds[j].  CD = D + D^T, so ranks that each own a row block compute
+ * half the work of ga_chamfer_all_pairs, all-gather the blocks and symmetrise
+ * (geometric_adv_b200/sharding.py). */
+int ga_chamfer_all_pairs_directed(int s, int n, const float* clouds, int row0, int rows, float* out, int mode,
+                                  ga_stream_t stream);
 
 /* ---- grouping: knn_point / selection_sort / group_point ------------------- */
 /* knn_point(k, xyz1, xyz2) of tf_grouping.py:48-75 in ONE kernel: xyz1 (b,n,3) is the

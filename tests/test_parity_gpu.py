@@ -299,4 +299,4 @@ def test_chamfer_per_cloud(ga, oracle):
     d1, _, d2, _ = ga.nn_distance(t(a), t(b))
     got = ga.chamfer_per_cloud(d1, d2).cpu().numpy()
     want = oracle.chamfer_per_cloud(d1.cpu().numpy(), d2.cpu().numpy())
-    np.testing.assert_allclose(got, want, rtol=1e-6)  # reduce_mean order is unpinned in the reference
+    np.testing.assert_allclose(got, want, rtol=2e-5)  # reduce_mean order is unpinned in the reference
