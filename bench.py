@@ -287,6 +287,30 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_step, t_fwd, t_bwd, t_e2e, t_sustained = [float(x) for x in times.tolist()]
 
+    # ---- the caller of the hot path: attack iterations per second (BASELINE metric, second half) ----
+    attack = None
+    if not args.no_attack:
+        from geometric_adv_b200.attack import steps_per_second
+        attack = {}
+        for ab in (50, 10):
+            sps, ms_it, _ = steps_per_second(ab, N, iters=40, warmup=8, use_cuda_graph=True, device=str(dev))
+            tt = torch.tensor([ms_it], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            attack["batch%d" % ab] = {"steps_per_s_per_gpu": 1000.0 / float(tt.item()), "ms_per_step": float(tt.item()),
+                                      "pairs_per_step_all_gpus": ab * world}
+        attack["what"] = ("one step = everything src/adv_ae.py:217-246 does once (update + metric re-evaluation + "
+                          "best-so-far), random-init PointNet AE, CUDA-graph replay; pairs sharded over GPUs")
+
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("nn_fwd_kernel_b50_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
     if rank == 0:
         pairs = float(B) * N * M * world
         per_gpu_pairs = float(B) * N * M
@@ -306,7 +330,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": "nn_fwd_kernel", "achieved": achieved, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
                          "flop_per_point_pair": FLOP_PER_PAIR, "ms_per_launch": t_fwd,
                          "peak_source": "ga_probe_fp32_peak (FFMA loop, measured on this device; "
                                         "MEASURED_PEAKS.json has no FP32 entry)"},
@@ -314,6 +338,7 @@ def run_ours(args):
                           "launch_floor_us": float(lf.value),
                           "bwd_algorithmic_GBps": 32.0 * B * (N + M) / (t_bwd * 1e-3) / 1e9,
                           "wall_s_timed_region": wall},
+            "attack": attack,
             "cpu_baseline": {"value": sb * N * M / cpu_t, "unit": UNIT, "cores": threads if O.have_ref() else 1,
                              "kind": kind,
                              "sample": "%d of the %d cloud pairs, one fwd+bwd pass" % (sb, B),
@@ -331,6 +356,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-attack", dest="no_attack", action="store_true", help="skip the attack steps/s leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

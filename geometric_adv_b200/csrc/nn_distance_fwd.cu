@@ -11,7 +11,8 @@
 // guarantees that the reference argmin lies in a tile whose filter minimum is
 // <= global filter minimum + W; only those tiles (almost always exactly one) are
 // re-evaluated in the reference arithmetic with the reference's strict-< /
-// lowest-index rule (three or more qualifying tiles: the whole chunk is rescanned).  Result: dist and idx are
+// lowest-index rule (three or more qualifying tiles, or more than two surviving
+// targets: the whole warp rescans the chunk for that query).  Result: dist and idx are
 // bit-identical to the selected reference arithmetic for every input, at ~3
 // FMA-pipe cycles per evaluated pair instead of ~9 issue slots.
 //

@@ -18,45 +18,11 @@ struct FwdCfg {
   static_assert(CH % T == 0 && (T & (T - 1)) == 0, "tile shapes");
 };
 
-// Re-evaluate one tile for one query: filter again per target, and evaluate the
-// survivors in the reference arithmetic.  Lexicographic (d, index) update so the
-// order in which tiles are refined does not matter.
-template <int T, int MODE>
-__device__ __forceinline__ void refine_tile(const float4* __restrict__ tp, int g0, int nt, float ax2, float ay2,
-                                            float az2, float qx, float qy, float qz, float thr, float& best,
-                                            int& besti) {
-  // Lanes of a warp usually refine DIFFERENT tiles; tiles are a multiple of 1 KB apart, so
-  // walking them in step would put all 32 lanes on the same banks.  Each lane starts at its
-  // own pair instead (the update below is order-independent).
-  const int rot = threadIdx.x & 31;
-#pragma unroll 4
-  for (int i = 0; i < T / 2; i++) {
-    const int pp = (i + rot) & (T / 2 - 1);
-    const float4 u = tp[2 * pp];
-    const float4 v = tp[2 * pp + 1];
-    const float2 f = filter_pair(u, v, ax2, ay2, az2);
-    if (fminf(f.x, f.y) > thr) continue;  // NaN threshold falls through
-    const int g = g0 + 2 * pp;
-    if (!(f.x > thr) && g < nt) {
-      const float d = sqdist<MODE>(u.x, u.z, v.x, qx, qy, qz);
-      if (d < best || (d == best && g < besti)) {
-        best = d;
-        besti = g;
-      }
-    }
-    if (!(f.y > thr) && g + 1 < nt) {
-      const float d = sqdist<MODE>(u.y, u.w, v.y, qx, qy, qz);
-      if (d < best || (d == best && g + 1 < besti)) {
-        best = d;
-        besti = g + 1;
-      }
-    }
-  }
-}
-
-// Same walk as refine_tile, but only RECORDS which targets pass the filter (first two
-// indices + count, branch-free), so that all lanes stay in step; the exact evaluation
-// happens afterwards, once, for every lane together.
+// Walk one tile for one query and RECORD which targets pass the filter (first two indices +
+// count, branch-free), so that all lanes stay in step; the exact evaluation happens afterwards,
+// once, for every lane together.  Lanes of a warp usually refine DIFFERENT tiles; tiles are a
+// multiple of 512 B apart, so walking them in step would put all 32 lanes on the same banks:
+// each lane starts at its own pair instead.
 template <int T>
 __device__ __forceinline__ void scan_tile_candidates(const float4* __restrict__ tp, int g0, int nt, float ax2,
                                                      float ay2, float az2, float thr, int& cnt, int& ca,
@@ -90,6 +56,48 @@ __device__ __forceinline__ void eval_candidate(const float4* __restrict__ tgt, i
   if (d < best || (d == best && g < besti)) {
     best = d;
     besti = g;
+  }
+}
+
+// Rare path, whole warp for ONE query: every lane filters a strided share of the staged
+// chunk, survivors are evaluated in the reference arithmetic, and the 32 partial results are
+// merged by (value, index).  Used when three or more tiles fall inside the window or more than
+// two targets survive (exact ties, degenerate or non-finite data).  A single lane walking the
+// chunk alone would take as long as the whole normal search of its warp and stall the CTA.
+template <int MODE>
+__device__ __forceinline__ void warp_exact_scan(const float4* __restrict__ tgt, int c0, int nt, int npair,
+                                                float qx, float qy, float qz, float ax2, float ay2, float az2,
+                                                float thr, float& b, int& bi, int lane) {
+  b = __int_as_float(0x7f800000);
+  bi = 0x7fffffff;
+  for (int p = lane; p < npair; p += 32) {
+    const float4 u = tgt[2 * p];
+    const float4 v = tgt[2 * p + 1];
+    const float2 f = filter_pair(u, v, ax2, ay2, az2);
+    const int g = c0 + 2 * p;
+    if (!(f.x > thr) && g < nt) {
+      const float d = sqdist<MODE>(u.x, u.z, v.x, qx, qy, qz);
+      if (d < b || (d == b && g < bi)) {
+        b = d;
+        bi = g;
+      }
+    }
+    if (!(f.y > thr) && g + 1 < nt) {
+      const float d = sqdist<MODE>(u.y, u.w, v.y, qx, qy, qz);
+      if (d < b || (d == b && g + 1 < bi)) {
+        b = d;
+        bi = g + 1;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+    const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < b || (ob == b && obi < bi)) {
+      b = ob;
+      bi = obi;
+    }
   }
 }
 
@@ -132,6 +140,7 @@ __device__ __forceinline__ void load_queries(QueryState<Cfg::kQ>& s, const float
 
 // Search one staged chunk (targets [c0, c0 + ntile*T) of a cloud with nt points).
 // bm_run: max |coordinate| over all targets staged so far (including this chunk).
+// Must be called by whole, converged warps (it uses warp collectives).
 template <class Cfg, int MODE>
 __device__ __forceinline__ void search_chunk(QueryState<Cfg::kQ>& s, const float4* __restrict__ tgt, int c0, int nt,
                                              int ntile, float bm_run) {
@@ -158,41 +167,45 @@ __device__ __forceinline__ void search_chunk(QueryState<Cfg::kQ>& s, const float
   });
 
   // ---- phase 2: refine the qualifying tiles in the reference arithmetic -----
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < Q; j++) {
-    if (!s.valid[j]) continue;
-    s.m1g[j] = fminf(s.m1g[j], c1[j]);
-    const float thr = s.m1g[j] + filter_window(s.qabs[j], bm_run);
-    const bool all_tiles = !(c3[j] > thr);  // three or more tiles in the window, or non-finite data
-    const bool t1 = !(c1[j] > thr), t2 = !(c2[j] > thr);
-    int cnt = 0, ca = 0, cb = 0;
-    if (all_tiles) {
-      for (int tile = 0; tile < ntile; tile++)
-        scan_tile_candidates<T>(tgt + (size_t)tile * T, c0 + tile * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr, cnt,
-                                ca, cb);
-    } else {
-      if (t1)
-        scan_tile_candidates<T>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
-                                cnt, ca, cb);
-      if (t2)
-        scan_tile_candidates<T>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
-                                cnt, ca, cb);
+    float thr = 0.0f;
+    bool hard = false;  // needs the cooperative scan
+    if (s.valid[j]) {
+      s.m1g[j] = fminf(s.m1g[j], c1[j]);
+      thr = s.m1g[j] + filter_window(s.qabs[j], bm_run);
+      hard = !(c3[j] > thr);  // three or more tiles in the window, or non-finite data
+      if (!hard) {
+        int cnt = 0, ca = 0, cb = 0;
+        if (!(c1[j] > thr))
+          scan_tile_candidates<T>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
+                                  cnt, ca, cb);
+        if (!(c2[j] > thr))
+          scan_tile_candidates<T>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
+                                  cnt, ca, cb);
+        // the usual case: one or two survivors, evaluated by all lanes in step
+        if (cnt >= 1 && cnt <= 2) eval_candidate<MODE>(tgt, c0, ca, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+        if (cnt == 2) eval_candidate<MODE>(tgt, c0, cb, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+        hard = cnt > 2;  // many survivors: exact ties or degenerate data
+      }
     }
-    if (cnt <= 2) {  // the usual case: one or two survivors, evaluated by all lanes in step
-      if (cnt >= 1) eval_candidate<MODE>(tgt, c0, ca, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
-      if (cnt >= 2) eval_candidate<MODE>(tgt, c0, cb, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
-    } else {         // many survivors (ties, degenerate or non-finite data): walk again, evaluating inline
-      if (all_tiles) {
-        for (int tile = 0; tile < ntile; tile++)
-          refine_tile<T, MODE>(tgt + (size_t)tile * T, c0 + tile * T, nt, s.ax2[j], s.ay2[j], s.az2[j], s.qx[j],
-                               s.qy[j], s.qz[j], thr, s.best[j], s.besti[j]);
-      } else {
-        if (t1)
-          refine_tile<T, MODE>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], s.qx[j],
-                               s.qy[j], s.qz[j], thr, s.best[j], s.besti[j]);
-        if (t2)
-          refine_tile<T, MODE>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], s.qx[j],
-                               s.qy[j], s.qz[j], thr, s.best[j], s.besti[j]);
+    // rare: the whole warp serves the flagged queries one at a time
+    unsigned pending = __ballot_sync(0xffffffffu, hard);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const float bqx = __shfl_sync(0xffffffffu, s.qx[j], src), bqy = __shfl_sync(0xffffffffu, s.qy[j], src),
+                  bqz = __shfl_sync(0xffffffffu, s.qz[j], src);
+      const float bax = __shfl_sync(0xffffffffu, s.ax2[j], src), bay = __shfl_sync(0xffffffffu, s.ay2[j], src),
+                  baz = __shfl_sync(0xffffffffu, s.az2[j], src);
+      const float bthr = __shfl_sync(0xffffffffu, thr, src);
+      float b;
+      int bi;
+      warp_exact_scan<MODE>(tgt, c0, nt, ntile * (T / 2), bqx, bqy, bqz, bax, bay, baz, bthr, b, bi, lane);
+      if (lane == src && (b < s.best[j] || (b == s.best[j] && bi < s.besti[j]))) {
+        s.best[j] = b;
+        s.besti[j] = bi;
       }
     }
   }

@@ -208,6 +208,31 @@ def test_host_entry_point_equals_device_entry_point(ga):
     assert all(bits_equal(x.cpu().numpy(), y.numpy()) for x, y in zip(gdev, ghost))
 
 
+def test_fwd_bwd_host_entry_point_chunked(ga):
+    """ga_nn_distance_fwd_bwd_host (what bench.py's e2e leg calls): chunked over two streams,
+    results identical to the device entry points."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    for b in (1, 5, 20):
+        n, m = 600, 500
+        a, c = cloud(90 + b, (b, n, 3)), cloud(91 + b, (b, m, 3))
+        gd1 = np.random.default_rng(b).standard_normal((b, n)).astype(np.float32)
+        gd2 = np.random.default_rng(b + 1).standard_normal((b, m)).astype(np.float32)
+        h = [torch.from_numpy(x).pin_memory() for x in (a, c, gd1, gd2)]
+        d1 = torch.empty(b, n).pin_memory(); i1 = torch.empty(b, n, dtype=torch.int32).pin_memory()
+        d2 = torch.empty(b, m).pin_memory(); i2 = torch.empty(b, m, dtype=torch.int32).pin_memory()
+        o1 = torch.empty(b, n, 3).pin_memory(); o2 = torch.empty(b, m, 3).pin_memory()
+        p = ctypes.c_void_p
+        _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, p(h[0].data_ptr()), p(h[1].data_ptr()),
+                                                   p(h[2].data_ptr()), p(h[3].data_ptr()), p(d1.data_ptr()),
+                                                   p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()),
+                                                   p(o1.data_ptr()), p(o2.data_ptr()), 0))
+        dev = ga.nn_distance(t(a), t(c))
+        g = ga.nn_distance_grad(t(a), t(c), t(gd1), dev[1], t(gd2), dev[3])
+        for x, y in zip((d1, i1, d2, i2, o1, o2), tuple(dev) + tuple(g)):
+            assert bits_equal(x.numpy(), y.cpu().numpy()), b
+
+
 # ------------------------------------------------------------------ backward
 def check_bwd(ga, oracle, a, b, gd1, i1, gd2, i2):
     g1, g2 = ga.nn_distance_grad(t(a), t(b), t(gd1), t(i1), t(gd2), t(i2))
