@@ -242,8 +242,8 @@ def run_ours(args):
     t_bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / K
     t_step = sum(e[0].elapsed_time(e[2]) for e in ev) / K
 
-    # sustained back-to-back loop (no flush) so the clock sampler sees load for >= 1 s
-    reps = max(200, int(1.0 / max(t_step * 1e-3, 1e-6)))
+    # sustained back-to-back loop (no flush) so the clock sampler sees load for >= 2 s
+    reps = max(200, int(2.0 / max(t_step * 1e-3, 1e-6)))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):

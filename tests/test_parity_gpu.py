@@ -209,12 +209,11 @@ def test_host_entry_point_equals_device_entry_point(ga):
 
 
 def test_fwd_bwd_host_entry_point_chunked(ga):
-    """ga_nn_distance_fwd_bwd_host (what bench.py's e2e leg calls): chunked over two streams,
-    results identical to the device entry points."""
+    """ga_nn_distance_fwd_bwd_host (what bench.py's e2e leg calls): results identical to the device
+    entry points; the two large shapes take the 2- and 4-chunk two-stream paths."""
     from geometric_adv_b200 import _lib
     lib = _lib.load()
-    for b in (1, 5, 20):
-        n, m = 600, 500
+    for b, n, m in ((1, 600, 500), (5, 600, 500), (20, 600, 500), (48, 4096, 4096), (160, 4096, 4000)):
         a, c = cloud(90 + b, (b, n, 3)), cloud(91 + b, (b, m, 3))
         gd1 = np.random.default_rng(b).standard_normal((b, n)).astype(np.float32)
         gd2 = np.random.default_rng(b + 1).standard_normal((b, m)).astype(np.float32)
