@@ -132,7 +132,15 @@ extern "C" int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const 
   a.b = b; a.n = n; a.m = m;
   a.xyz1 = xyz1; a.xyz2 = xyz2;
   a.dist1 = dist1; a.idx1 = idx1; a.dist2 = dist2; a.idx2 = idx2;
-  switch (g_fwd_variant) {
+  // Default: 4 queries per thread (FMA-pipe bound scan).  Small problems (few hundred query
+  // tiles, e.g. the B=1 calls of autoencoder.py:150-168) take 2 queries per thread instead:
+  // twice the CTAs to spread over the 148 SMs matters more than the LDS-bound inner loop.
+  int variant = g_fwd_variant;
+  if (variant == 0) {
+    const long long queries = (long long)b * ((long long)n + m);
+    variant = queries < 148LL * 2 * 512 ? 4 : 1;
+  }
+  switch (variant) {
 #define GA_FWD_CASE(ID, TH, QQ, TT, CC)                                                          \
   case ID: {                                                                                     \
     using Cfg = FwdCfg<TH, QQ, TT, CC>;                                                          \
@@ -140,17 +148,16 @@ extern "C" int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const 
     a.tiles2 = (m + Cfg::kQT - 1) / Cfg::kQT;                                                    \
     return launch_fwd<Cfg>(a, mode, st);                                                         \
   }
-    GA_FWD_CASE(1, 128, 4, 32, 2048)
     GA_FWD_CASE(2, 64, 4, 64, 2048)
     GA_FWD_CASE(3, 64, 2, 32, 2048)
     GA_FWD_CASE(4, 128, 2, 32, 2048)
-    GA_FWD_CASE(5, 64, 8, 32, 2048)
-    GA_FWD_CASE(6, 32, 8, 32, 2048)
+    GA_FWD_CASE(5, 64, 4, 32, 2048)
+    GA_FWD_CASE(6, 256, 4, 32, 2048)
     GA_FWD_CASE(7, 64, 4, 16, 2048)
     GA_FWD_CASE(8, 32, 4, 32, 2048)
-    GA_FWD_CASE(9, 64, 4, 32, 1024)
+    GA_FWD_CASE(9, 64, 2, 32, 1024)
     default:
-    GA_FWD_CASE(0, 64, 4, 32, 2048)
+    GA_FWD_CASE(1, 128, 4, 32, 2048)
 #undef GA_FWD_CASE
   }
 }
