@@ -15,6 +15,8 @@
 // one thread per output point walks its contributor list in ascending order with
 // unfused __fmul_rn/__fadd_rn.  Every output element is written exactly once, so
 // no memset is needed and the result is run-to-run reproducible.
+#include <atomic>
+
 #include "ga_common.cuh"
 
 namespace ga {
@@ -220,7 +222,17 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
     return GA_ERR_UNSUPPORTED;
   }
   const size_t smem = bwd_smem_bytes(lmax);
-  GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    // raise the opt-in shared-memory limit once per device to the largest size the kernel can ask for
+    static std::atomic<unsigned> done_mask{0};
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done_mask.load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bwd_smem_bytes(65536)));
+      done_mask.fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
+  }
   BwdArgs a;
   a.b = b; a.n = n; a.m = m;
   a.xyz1 = xyz1; a.xyz2 = xyz2;

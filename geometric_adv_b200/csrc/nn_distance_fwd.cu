@@ -23,6 +23,8 @@
 // constant) leaves room for rounding W and the threshold themselves.  Non-finite
 // or overflowing inputs make W = inf/NaN, every tile qualifies, and the kernel
 // degenerates to the plain reference scan (still exact).
+#include <atomic>
+
 #include "nn_search.cuh"
 
 namespace ga {
@@ -36,6 +38,12 @@ struct FwdArgs {
   float* dist2;
   int* idx2;
   int tiles1, tiles2;  // query tiles per cloud, direction 1->2 and 2->1
+  // optional second destination for every output (mapped pinned HOST memory: the host entry
+  // points let the kernel stream results over PCIe while it computes, instead of a D2H copy)
+  float* mdist1;
+  int* midx1;
+  float* mdist2;
+  int* midx2;
 };
 
 template <class Cfg, int MODE>
@@ -57,6 +65,8 @@ __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_kernel(const FwdArgs a) 
   const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
   float* odist = (rev ? a.dist2 : a.dist1) + (size_t)batch * nq;
   int* oidx = (rev ? a.idx2 : a.idx1) + (size_t)batch * nq;
+  float* mdist = rev ? a.mdist2 : a.mdist1;
+  int* midx = rev ? a.midx2 : a.midx1;
 
   QueryState<Q> s;
   load_queries<Cfg, MODE>(s, qpts, nq, qtile, tpts, tid);
@@ -76,6 +86,10 @@ __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_kernel(const FwdArgs a) 
     finish_query<Q>(s, j, d, i);
     odist[qi] = d;
     oidx[qi] = i;
+    if (mdist != nullptr) {
+      mdist[(size_t)batch * nq + qi] = d;
+      midx[(size_t)batch * nq + qi] = i;
+    }
   }
 }
 
@@ -90,10 +104,14 @@ static int launch_fwd(const FwdArgs& a, int mode, cudaStream_t st) {
   auto k0 = nn_fwd_kernel<Cfg, GA_MODE_CPU_EXACT>;
   auto k1 = nn_fwd_kernel<Cfg, GA_MODE_GPU_REF>;
   auto k = mode == GA_MODE_CPU_EXACT ? k0 : k1;
-  static thread_local bool attr_set[2] = {false, false};
-  if (!attr_set[mode]) {
-    GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-    attr_set[mode] = true;
+  {
+    static std::atomic<unsigned> done_mask[2];  // per mode, one bit per device
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done_mask[mode].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+      done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
   }
   k<<<(unsigned)jobs, Cfg::kThreads, Cfg::kSmem, st>>>(a);
   GA_LAUNCH_CHECK("nn_fwd_kernel");
@@ -104,9 +122,10 @@ int g_fwd_variant = 0;  // tuning hook (ga_set_tuning): 0 = default
 
 }  // namespace ga
 
-extern "C" int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1,
-                                  int* idx1, float* dist2, int* idx2, int mode, ga_stream_t stream) {
-  using namespace ga;
+namespace ga {
+int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1, int* idx1,
+                             float* dist2, int* idx2, float* mdist1, int* midx1, float* mdist2, int* midx2,
+                             int mode, ga_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) {
     set_error("ga_nn_distance_fwd: negative size (b=%d n=%d m=%d)", b, n, m);
     return GA_ERR_INVALID_ARGUMENT;
@@ -132,6 +151,7 @@ extern "C" int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const 
   a.b = b; a.n = n; a.m = m;
   a.xyz1 = xyz1; a.xyz2 = xyz2;
   a.dist1 = dist1; a.idx1 = idx1; a.dist2 = dist2; a.idx2 = idx2;
+  a.mdist1 = mdist1; a.midx1 = midx1; a.mdist2 = mdist2; a.midx2 = midx2;
   // Default: 4 queries per thread (FMA-pipe bound scan).  Small problems (few hundred query
   // tiles, e.g. the B=1 calls of autoencoder.py:150-168) take 2 queries per thread instead:
   // twice the CTAs to spread over the 148 SMs matters more than the LDS-bound inner loop.
@@ -160,4 +180,11 @@ extern "C" int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const 
     GA_FWD_CASE(1, 128, 4, 32, 2048)
 #undef GA_FWD_CASE
   }
+}
+}  // namespace ga
+
+extern "C" int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1,
+                                  int* idx1, float* dist2, int* idx2, int mode, ga_stream_t stream) {
+  return ga::nn_distance_fwd_mirrored(b, n, m, xyz1, xyz2, dist1, idx1, dist2, idx2, nullptr, nullptr, nullptr,
+                                      nullptr, mode, stream);
 }

@@ -208,19 +208,24 @@ def test_host_entry_point_equals_device_entry_point(ga):
     assert all(bits_equal(x.cpu().numpy(), y.numpy()) for x, y in zip(gdev, ghost))
 
 
-def test_fwd_bwd_host_entry_point_chunked(ga):
+@pytest.mark.parametrize("pinned,path", [(True, 0), (False, 0), (True, 2)])
+def test_fwd_bwd_host_entry_point(ga, pinned, path):
     """ga_nn_distance_fwd_bwd_host (what bench.py's e2e leg calls): results identical to the device
-    entry points; the two large shapes take the 2- and 4-chunk two-stream paths."""
+    entry points, for pinned and pageable caller memory (1-, 2- and 4-chunk two-stream copies) and
+    for the opt-in zero-copy path (ingest kernel, mirrored forward outputs, gradients written
+    straight to the host)."""
     from geometric_adv_b200 import _lib
     lib = _lib.load()
-    for b, n, m in ((1, 600, 500), (5, 600, 500), (20, 600, 500), (48, 4096, 4096), (160, 4096, 4000)):
+    lib.ga_set_tuning(2, path)
+    pin = (lambda x: x.pin_memory()) if pinned else (lambda x: x)
+    for b, n, m in ((1, 600, 500), (5, 601, 500), (20, 600, 503), (48, 4096, 4096), (160, 4096, 4000)):
         a, c = cloud(90 + b, (b, n, 3)), cloud(91 + b, (b, m, 3))
         gd1 = np.random.default_rng(b).standard_normal((b, n)).astype(np.float32)
         gd2 = np.random.default_rng(b + 1).standard_normal((b, m)).astype(np.float32)
-        h = [torch.from_numpy(x).pin_memory() for x in (a, c, gd1, gd2)]
-        d1 = torch.empty(b, n).pin_memory(); i1 = torch.empty(b, n, dtype=torch.int32).pin_memory()
-        d2 = torch.empty(b, m).pin_memory(); i2 = torch.empty(b, m, dtype=torch.int32).pin_memory()
-        o1 = torch.empty(b, n, 3).pin_memory(); o2 = torch.empty(b, m, 3).pin_memory()
+        h = [pin(torch.from_numpy(x)) for x in (a, c, gd1, gd2)]
+        d1 = pin(torch.empty(b, n)); i1 = pin(torch.empty(b, n, dtype=torch.int32))
+        d2 = pin(torch.empty(b, m)); i2 = pin(torch.empty(b, m, dtype=torch.int32))
+        o1 = pin(torch.empty(b, n, 3)); o2 = pin(torch.empty(b, m, 3))
         p = ctypes.c_void_p
         _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, p(h[0].data_ptr()), p(h[1].data_ptr()),
                                                    p(h[2].data_ptr()), p(h[3].data_ptr()), p(d1.data_ptr()),
@@ -229,7 +234,8 @@ def test_fwd_bwd_host_entry_point_chunked(ga):
         dev = ga.nn_distance(t(a), t(c))
         g = ga.nn_distance_grad(t(a), t(c), t(gd1), dev[1], t(gd2), dev[3])
         for x, y in zip((d1, i1, d2, i2, o1, o2), tuple(dev) + tuple(g)):
-            assert bits_equal(x.numpy(), y.cpu().numpy()), b
+            assert bits_equal(x.numpy(), y.cpu().numpy()), (b, n, m, pinned, path)
+    lib.ga_set_tuning(2, 0)
 
 
 # ------------------------------------------------------------------ backward
