@@ -10,4 +10,6 @@ from .ops import (GA_MODE_CPU_EXACT, GA_MODE_GPU_REF, chamfer_3DDist, chamfer_3D
                   chamfer_per_cloud, group_point, knn_dists, knn_point, launch_count, nn_distance,
                   nn_distance_grad, select_top_k, set_default_mode)
 
+from . import attack, defense, sharding  # noqa: E402,F401  (host loops either side of the hot path)
+
 __version__ = "0.1.0"

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ga_group_point": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ga_knn_dists": (_i, [_i, _i, _i, _p, _p, _p]),
     "ga_knn_dists_host": (_i, [_i, _i, _i, _p, _p]),
+    "ga_split_by_threshold": (_i, [_i, _i, _p, _p, C.c_float, _p, _p, _p, _p, _p]),
     "ga_set_tuning": (_i, [_i, _i]),
     "ga_probe_fp32_peak": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p]),
     "ga_probe_launch_floor": (_i, [_i, C.POINTER(C.c_float), _p]),

@@ -117,3 +117,21 @@ def shard_pairs(sources, targets, group=None):
     world, rank = _world(group)
     lo, hi = shard_range(sources.shape[0], world, rank)
     return sources[lo:hi], targets[lo:hi], (lo, hi)
+
+
+def save_chamfer_nn_files(data_path, chamfer_dist_mat, slice_idx, file_name_parts=("test", "set", "13l")):
+    """Write the two stage files the downstream reference scripts read, with the reference's names,
+    dtypes and shapes (prepare_indices_for_attack.py:84-86,144-164; consumer
+    src/adversary_utils.py:51-63): chamfer_dist_mat_complete_<parts>.npy float32 (S,S) and
+    chamfer_nn_idx_complete_<parts>.npy int16 (S,S)."""
+    import os
+    dm = chamfer_dist_mat.detach().cpu().numpy() if isinstance(chamfer_dist_mat, torch.Tensor) else np.asarray(
+        chamfer_dist_mat)
+    dm = dm.astype(np.float32)
+    assert dm.min() >= 0, "the chamfer_dist_mat matrix was not filled correctly"
+    tail = "_".join(file_name_parts)
+    p1 = os.path.join(data_path, "chamfer_dist_mat_complete_" + tail + ".npy")
+    p2 = os.path.join(data_path, "chamfer_nn_idx_complete_" + tail + ".npy")
+    np.save(p1, dm)
+    np.save(p2, sort_dist_mat(dm, slice_idx))
+    return p1, p2

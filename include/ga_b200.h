@@ -142,6 +142,14 @@ int ga_group_point(int b, int n, int c, int m, int nsample, const float* points,
 int ga_knn_dists(int b, int n, int k, const float* pc, float* out, ga_stream_t stream);
 int ga_knn_dists_host(int b, int n, int k, const float* pc, float* out);
 
+/* get_outlier_pc_inlier_pc (src/adversary_utils.py:149-178) for a whole batch: per cloud, the points
+ * with score > thresh go (in index order) to outlier_pc / outlier_idx, those with score <= thresh to
+ * inlier_pc; a part that is neither empty nor the whole cloud is padded with its last point, empty
+ * parts and the tail of outlier_idx are zero; outlier_num (b) counts.  The surface defense feeds it the
+ * mean of the first two kNN distances and 0.04 (defender/run_defense_surface.py:187-191). */
+int ga_split_by_threshold(int b, int n, const float* pc, const float* score, float thresh, float* outlier_pc,
+                          int* outlier_idx, int* outlier_num, float* inlier_pc, ga_stream_t stream);
+
 /* ---- measurement helpers --------------------------------------------------- */
 /* Dependent-free FFMA loop on every SM; returns achieved FP32 TFLOP/s (2 flop per
  * FFMA lane) through *tflops.  bench.py uses it as the FP32 roofline denominator,

@@ -211,3 +211,36 @@ void ga_oracle_knn_dists(int b, int n, int k, const float* pc, float* out) {
   free(val);
   free(idx);
 }
+
+/* src/adversary_utils.py:149-178 (get_outlier_pc_inlier_pc): per cloud, points whose score exceeds
+ * the threshold vs the rest, index order kept; a part that is neither empty nor the whole cloud
+ * is padded with its last point; a NaN score falls into neither part. */
+void ga_oracle_split_by_threshold(int b, int n, const float* pc, const float* score, float thresh,
+                                  float* outlier_pc, int* outlier_idx, int* outlier_num, float* inlier_pc) {
+  memset(outlier_pc, 0, sizeof(float) * (size_t)b * n * 3);
+  memset(inlier_pc, 0, sizeof(float) * (size_t)b * n * 3);
+  memset(outlier_idx, 0, sizeof(int) * (size_t)b * n);
+  for (int l = 0; l < b; l++) {
+    const float* p = pc + (size_t)l * n * 3;
+    const float* s = score + (size_t)l * n;
+    float* op = outlier_pc + (size_t)l * n * 3;
+    float* ip = inlier_pc + (size_t)l * n * 3;
+    int no = 0, ni = 0;
+    for (int i = 0; i < n; i++) {
+      if (s[i] > thresh) {
+        memcpy(op + (size_t)no * 3, p + (size_t)i * 3, 3 * sizeof(float));
+        outlier_idx[(size_t)l * n + no] = i;
+        no++;
+      }
+      if (s[i] <= thresh) {
+        memcpy(ip + (size_t)ni * 3, p + (size_t)i * 3, 3 * sizeof(float));
+        ni++;
+      }
+    }
+    outlier_num[l] = no;
+    if (no > 0 && no < n)
+      for (int i = no; i < n; i++) memcpy(op + (size_t)i * 3, op + (size_t)(no - 1) * 3, 3 * sizeof(float));
+    if (ni > 0 && ni < n)
+      for (int i = ni; i < n; i++) memcpy(ip + (size_t)i * 3, ip + (size_t)(ni - 1) * 3, 3 * sizeof(float));
+  }
+}

@@ -151,6 +151,19 @@ def knn_dists(pc, k):
     return out
 
 
+def split_by_threshold(pc, score, thresh):
+    """src/adversary_utils.py:149-178 -> outlier_pc, outlier_idx, outlier_num, inlier_pc."""
+    pc, score = _f32(pc), _f32(score)
+    b, n, _ = pc.shape
+    opc = np.empty((b, n, 3), np.float32)
+    ipc = np.empty((b, n, 3), np.float32)
+    oidx = np.empty((b, n), np.int32)
+    onum = np.empty((b,), np.int32)
+    lib().ga_oracle_split_by_threshold(b, n, _fp(pc), _fp(score), C.c_float(thresh), _fp(opc), _ip(oidx),
+                                       _ip(onum), _fp(ipc))
+    return opc, oidx, onum, ipc
+
+
 def knn_dists_numpy(pc, k):
     """The reference's numpy fallback, restated with numpy itself:
     src/general_utils.py:94-106 (get_dist_mat) + get_knn_dists_per_point.py:125-137."""

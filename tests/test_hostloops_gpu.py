@@ -106,3 +106,67 @@ def test_attack_pairs_shards_equal_the_whole():
     # a different batch size changes the cuBLAS/cuDNN kernels of the AE, not the attack itself
     m3, _ = attack_pairs(ae, src, tgt, batch_size=3, num_iterations=6, num_iterations_thresh=3)
     assert torch.allclose(m3[:, 4], m[:, 4], rtol=1e-3)
+
+
+def test_outlier_inlier_split_matches_the_reference_loop(ga, oracle):
+    """get_outlier_pc_inlier_pc (adversary_utils.py:149-178), batched on the GPU: bit-equal."""
+    from geometric_adv_b200 import defense
+    rng = np.random.default_rng(0)
+    pc = cloud(7, (6, 700, 3))
+    score = rng.random((6, 700), dtype=np.float32) * np.float32(0.08)
+    score[1] = 1.0            # every point an outlier
+    score[2] = 0.0            # none
+    score[3, 5] = np.nan      # belongs to neither part
+    score[4, :] = 0.04        # exactly at the threshold: inlier (<=)
+    got = defense.get_outlier_pc_inlier_pc(t(pc), t(score), 0.04)
+    want = oracle.split_by_threshold(pc, score, 0.04)
+    assert bits_equal(got[0].cpu().numpy(), want[0]) and bits_equal(got[3].cpu().numpy(), want[3])
+    assert np.array_equal(got[1].cpu().numpy(), want[1].astype(np.int16))
+    assert np.array_equal(got[2].cpu().numpy(), want[2].astype(np.int16))
+    assert got[1].dtype == torch.int16 and got[2].dtype == torch.int16
+
+
+def test_surface_defense_pipeline(ga, oracle):
+    """kNN distances -> mean of the first two -> threshold -> filtered clouds -> batched loss per cloud."""
+    from geometric_adv_b200 import defense
+    from geometric_adv_b200.attack import PointNetAE
+    torch.manual_seed(0)
+    ae = PointNetAE(512).to(DEV).eval()
+    src = cloud(8, (5, 512, 3))
+    adv = src.copy()
+    adv[:, :20] += np.float32(0.3)  # a few points pushed off the surface
+    score = defense.knn_dists_mean(t(adv), 8, 2)
+    want_score = oracle.knn_dists(adv, 8)[:, :, :2]
+    np.testing.assert_allclose(score.cpu().numpy(), (want_score[..., 0] + want_score[..., 1]) / 2, rtol=1e-6)
+    recon = lambda x: ae(x)[0]
+    defended, err, (opc, oidx, onum) = defense.surface_defense(t(adv), recon, t(src), knn_dist_thresh=0.15)
+    assert int(onum.min()) >= 1 and defended.shape == (5, 512, 3) and err.shape == (5,)
+    # batched get_loss_per_pc == the reference's one-cloud-at-a-time loop
+    with torch.no_grad():
+        one = torch.stack([defense.get_loss_per_pc(recon, defended[i:i + 1], t(src)[i:i + 1])[0] for i in range(5)])
+    assert torch.allclose(err, one, rtol=1e-5)
+
+
+def test_foldingnet_call_sites(ga):
+    """foldingnet.py:209-238 (dense Chamfer, N != M) and prepare_graph.py:45-73 (KDTree k=16 + cov)."""
+    from geometric_adv_b200 import callsites
+    x = t(cloud(9, (3, 2025, 3))).requires_grad_(True)   # FoldingNet output: 45^2 points
+    y = t(cloud(10, (3, 2048, 3)))
+    loss = callsites.foldingnet_chamfer_distance(x, y)
+    loss.backward()
+    xd = x.detach()
+    d = ((xd[:, None, :, :] - y[:, :, None, :]) ** 2).sum(3)            # the reference's dense form
+    want = d.min(1)[0].mean() + d.min(2)[0].mean()
+    assert torch.allclose(loss, want, rtol=1e-5)
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all())
+    pc = cloud(11, (2, 700, 3))
+    idx, dist, cov = callsites.foldingnet_knn_graph(t(pc), 16)
+    from sklearn.neighbors import KDTree
+    for i in range(2):
+        nd, ni = KDTree(pc[i], leaf_size=30).query(pc[i], k=17, return_distance=True)
+        assert np.array_equal(idx[i].cpu().numpy(), ni[:, 1:])
+        np.testing.assert_allclose(dist[i].cpu().numpy(), nd, rtol=1e-5, atol=1e-7)
+        c = np.stack([np.cov(pc[i][ni[j, 1:]].T).reshape(-1) for j in range(0, 700, 50)])
+        np.testing.assert_allclose(cov[i].cpu().numpy()[::50], c, rtol=1e-4, atol=1e-7)
+    edges = callsites.knn_edges(idx)
+    assert edges[0].shape[0] == 2 and edges[0].shape[1] >= 700 * 16

@@ -111,3 +111,17 @@ def test_sort_dist_mat_and_consumer_view():
     t = nearest_targets(nn, slice_idx, 0, 1, 2, 3)
     blk = dm[1, slice_idx[2]:slice_idx[3]]
     assert t.tolist() == np.argsort(blk, kind="stable")[:3].tolist()
+
+
+def test_stage_files_have_the_reference_names_and_dtypes(tmp_path):
+    from geometric_adv_b200.sharding import save_chamfer_nn_files
+    rng = np.random.default_rng(1)
+    dm = rng.random((9, 9)).astype(np.float32)
+    dm = dm + dm.T
+    np.fill_diagonal(dm, 0)
+    p1, p2 = save_chamfer_nn_files(str(tmp_path), torch.from_numpy(dm), [0, 4, 9])
+    assert p1.endswith("chamfer_dist_mat_complete_test_set_13l.npy")
+    assert p2.endswith("chamfer_nn_idx_complete_test_set_13l.npy")
+    a, b = np.load(p1), np.load(p2)
+    assert a.dtype == np.float32 and a.shape == (9, 9) and np.array_equal(a, dm)
+    assert b.dtype == np.int16 and b.shape == (9, 9) and b.min() >= 0
