@@ -8,7 +8,7 @@ defense and evaluation scripts call.
 """
 from .ops import (GA_MODE_CPU_EXACT, GA_MODE_GPU_REF, chamfer_3DDist, chamfer_3DFunction, chamfer_all_pairs,
                   chamfer_per_cloud, group_point, knn_dists, knn_point, launch_count, nn_distance,
-                  nn_distance_grad, select_top_k, set_default_mode)
+                  nn_distance_grad, select_top_k, set_default_mode, set_pruning)
 
 from . import attack, defense, sharding  # noqa: E402,F401  (host loops either side of the hot path)
 

@@ -30,6 +30,8 @@ SIGNATURES = {
     "ga_check_selection_sort": (_i, [_i, _i, _ll]),
     "ga_check_group_point": (_i, [_i, _ll, _i, _ll]),
     "ga_nn_distance_fwd": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "ga_nn_distance_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "ga_nn_distance_fwd_ws": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, C.c_size_t, _p]),
     "ga_nn_distance_fwd_host": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i]),
     "ga_nn_distance_bwd": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ga_nn_distance_bwd_host": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -13,6 +13,7 @@ extern int g_fwd_variant;  // nn_distance_fwd.cu
 extern int g_knn_variant;  // grouping.cu
 extern int g_host_path;    // host_api.cu
 extern int g_host_chunks;  // host_api.cu
+extern int g_sorted_variant;  // nn_distance_sorted.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -93,6 +94,10 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 3) {
     ga::g_host_chunks = value;
+    return GA_OK;
+  }
+  if (key == 4) {
+    ga::g_sorted_variant = value;
     return GA_OK;
   }
   ga::set_error("ga_set_tuning: unknown key %d", key);

@@ -176,6 +176,12 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
     GA_FWD_CASE(7, 64, 4, 16, 2048)
     GA_FWD_CASE(8, 32, 4, 32, 2048)
     GA_FWD_CASE(9, 64, 2, 32, 1024)
+    GA_FWD_CASE(10, 128, 3, 32, 2048)
+    GA_FWD_CASE(11, 64, 4, 32, 1024)
+    GA_FWD_CASE(12, 32, 4, 32, 1024)
+    GA_FWD_CASE(13, 64, 3, 32, 2048)
+    GA_FWD_CASE(14, 96, 4, 32, 2048)
+    GA_FWD_CASE(15, 160, 4, 32, 2048)
     default:
     GA_FWD_CASE(1, 128, 4, 32, 2048)
 #undef GA_FWD_CASE

@@ -24,11 +24,23 @@ from ._lib import GA_MODE_CPU_EXACT, GA_MODE_GPU_REF
 
 __all__ = [
     "nn_distance", "nn_distance_grad", "chamfer_3DDist", "chamfer_3DFunction", "knn_point", "select_top_k",
-    "group_point", "knn_dists", "chamfer_per_cloud", "chamfer_all_pairs", "set_default_mode", "launch_count",
+    "group_point", "knn_dists", "chamfer_per_cloud", "chamfer_all_pairs", "set_default_mode", "set_pruning",
+    "launch_count",
     "GA_MODE_CPU_EXACT", "GA_MODE_GPU_REF",
 ]
 
 _default_mode = GA_MODE_CPU_EXACT
+_pruning = False
+
+
+def set_pruning(enabled):
+    """Opt in to the spatially pruned forward (ga_nn_distance_fwd_ws: Morton-ordered clouds, tiles
+    skipped by box bounds; same bits) for CUDA clouds of 256..2048 points.  Off by default: on
+    uniformly random 2048-point clouds a warp's 128 queries still need 60 % of the tiles and the
+    sort costs 27 us, so it is slower at B=50 (103 vs 78 us) and ~11 % faster at B=512
+    (profiles/r01_tune.json); clouds with spatial structure and larger batches are where it pays."""
+    global _pruning
+    _pruning = bool(enabled)
 
 
 def set_default_mode(mode):
@@ -96,9 +108,17 @@ def _nn_distance_fwd(xyz1, xyz2, mode):
     dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
     idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
     if dev.type == "cuda":
+        ws_bytes = lib.ga_nn_distance_workspace_bytes(b, n, m) if (_pruning and min(n, m) >= 256) else 0
         with _Guard(dev):
-            rc = lib.ga_nn_distance_fwd(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(),
-                                        idx1.data_ptr(), dist2.data_ptr(), idx2.data_ptr(), mode, _stream(xyz1))
+            if ws_bytes:
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)  # scratch, no state kept
+                rc = lib.ga_nn_distance_fwd_ws(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(),
+                                               idx1.data_ptr(), dist2.data_ptr(), idx2.data_ptr(), mode,
+                                               ws.data_ptr(), ws_bytes, _stream(xyz1))
+            else:
+                rc = lib.ga_nn_distance_fwd(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(),
+                                            idx1.data_ptr(), dist2.data_ptr(), idx2.data_ptr(), mode,
+                                            _stream(xyz1))
     else:
         rc = lib.ga_nn_distance_fwd_host(b, n, m, xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(),
                                          idx1.data_ptr(), dist2.data_ptr(), idx2.data_ptr(), mode)

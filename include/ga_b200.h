@@ -79,6 +79,17 @@ int ga_nn_distance_fwd(int b, int n, int m, const float* xyz1, const float* xyz2
 int ga_nn_distance_fwd_host(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1, int* idx1,
                             float* dist2, int* idx2, int mode);
 
+/* Same result, fewer evaluations: with a caller-provided scratch buffer the clouds are first put
+ * in Morton order (one small kernel), and each warp of 128 spatially adjacent queries then visits
+ * the 32-point target tiles in ascending box-distance order and stops as soon as no remaining tile
+ * can hold a candidate (exact; see nn_distance_sorted.cu).  `workspace` must hold
+ * ga_nn_distance_workspace_bytes(b,n,m) bytes of device memory; it carries no state between
+ * calls.  Without a workspace, or for clouds outside 256..2048 points, this is ga_nn_distance_fwd. */
+size_t ga_nn_distance_workspace_bytes(int b, int n, int m);
+int ga_nn_distance_fwd_ws(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1, int* idx1,
+                          float* dist2, int* idx2, int mode, void* workspace, size_t workspace_bytes,
+                          ga_stream_t stream);
+
 /* Replaces NmDistanceGradKernelLauncher (tf_nndistance.cpp:208, tf_nndistance_g.cu:152-157),
  * chamfer_cuda_backward (chamfer_cuda.cpp:12, chamfer3D.cu:176-195) and
  * NnDistanceGradOp's CPU loops (tf_nndistance.cpp:122-163).  Atomic-free: every

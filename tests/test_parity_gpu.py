@@ -27,12 +27,19 @@ def run_fwd(ga, a, b, mode=0):
 
 
 def check_fwd(ga, oracle, a, b, mode=0):
-    got = run_fwd(ga, a, b, mode)
+    """Both forward paths (plain scan, and Morton-ordered scan with tile skipping) against the oracle."""
     want = oracle.nn_distance(a, b, mode)
     names = ["dist1", "idx1", "dist2", "idx2"]
-    for nme, g, w in zip(names, got, want):
-        assert bits_equal(g, w), "%s differs (shape %s vs %s, mode %d): %d mismatches" % (
-            nme, a.shape, b.shape, mode, int(np.sum(g != w)))
+    got = None
+    for pruning in (False, True):
+        ga.set_pruning(pruning)
+        try:
+            got = run_fwd(ga, a, b, mode)
+        finally:
+            ga.set_pruning(False)
+        for nme, g, w in zip(names, got, want):
+            assert bits_equal(g, w), "%s differs (shape %s vs %s, mode %d, pruning %s): %d mismatches" % (
+                nme, a.shape, b.shape, mode, pruning, int(np.sum(g != w)))
     return got
 
 

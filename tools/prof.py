@@ -32,6 +32,12 @@ for _ in range(3):
         _lib.check(lib.ga_nn_distance_bwd(B, N, N, p(x1.data_ptr()), p(x2.data_ptr()), p(g1.data_ptr()),
                                           p(i1.data_ptr()), p(g1.data_ptr()), p(i2.data_ptr()), p(o1.data_ptr()),
                                           p(o2.data_ptr()), p(st)))
+    if what == "sorted":
+        wsb = lib.ga_nn_distance_workspace_bytes(B, N, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _lib.check(lib.ga_nn_distance_fwd_ws(B, N, N, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()),
+                                             p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()), 0,
+                                             p(ws.data_ptr()), wsb, p(st)))
     if what in ("knn", "all"):
         _lib.check(lib.ga_knn_dists(B, N, 10, p(x1.data_ptr()), p(kd.data_ptr()), p(st)))
 torch.cuda.synchronize()

@@ -1,0 +1,26 @@
+"""Small driver that touches every kernel once (for compute-sanitizer; development tool)."""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import geometric_adv_b200 as ga
+from geometric_adv_b200 import defense
+dev = "cuda:0"
+rng = np.random.default_rng(0)
+def cl(b, n): return torch.from_numpy((rng.random((b, n, 3), dtype=np.float32) - 0.5).astype(np.float32)).to(dev)
+for (b, n, m) in [(2, 300, 517), (1, 2048, 2048), (1, 2500, 100)]:
+    x1, x2 = cl(b, n).requires_grad_(True), cl(b, m).requires_grad_(True)
+    for pr in (False, True):
+        ga.set_pruning(pr)
+        d1, i1, d2, i2 = ga.nn_distance(x1, x2)
+    ga.set_pruning(False)
+    (d1.mean() + d2.mean()).backward()
+g = torch.from_numpy((rng.integers(0, 3, (1, 300, 3)) * 0.5).astype(np.float32)).to(dev)  # ties -> cooperative paths
+ga.nn_distance(g, g); ga.knn_point(5, g, g); ga.knn_point(40, g, g)
+pc = cl(2, 700)
+ga.knn_dists(pc, 10); v, i = ga.knn_point(11, pc, pc); ga.knn_point(17, pc, pc); ga.knn_point(30, cl(1, 2300), cl(1, 50))
+ga.group_point(pc, i); ga.select_top_k(3, torch.rand(2, 9, 50, device=dev))
+ga.chamfer_all_pairs(cl(5, 300)); ga.chamfer_per_cloud(d1.detach(), d2.detach())
+defense.get_outlier_pc_inlier_pc(pc, torch.rand(2, 700, device=dev), 0.5)
+h = torch.rand(2, 64, 3); ga.nn_distance(h, h); ga.knn_dists(h, 3)
+torch.cuda.synchronize(); print("driver ok")

@@ -66,7 +66,7 @@ for (b, n, m) in [(50, 2048, 2048), (10, 2048, 2048), (1, 2048, 2048), (512, 204
     pairs = float(b) * n * m
     key = "fwd_b%d" % b
     out[key] = {}
-    for v in range(0, 10):
+    for v in range(0, 16):
         lib.ga_set_tuning(0, v)
         r = timeit(lambda: lib.ga_nn_distance_fwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()),
                                                   p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()), 0, p(st)))
@@ -77,6 +77,17 @@ for (b, n, m) in [(50, 2048, 2048), (10, 2048, 2048), (1, 2048, 2048), (512, 204
     r = timeit(lambda: lib.ga_nn_distance_fwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()),
                                               p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()), 1, p(st)))
     out[key]["variant0_mode1"] = r
+    wsb = lib.ga_nn_distance_workspace_bytes(b, n, m)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+    for v in range(5):
+        lib.ga_set_tuning(4, v)
+        r = timeit(lambda: lib.ga_nn_distance_fwd_ws(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()),
+                                                     p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()), 0,
+                                                     p(ws.data_ptr()), wsb, p(st)))
+        r["TFLOPs_8flop"] = 8 * pairs / (r["min_ms"] * 1e-3) / 1e12
+        out[key]["sorted_variant%d" % v] = r
+        print(key, "sorted (pruned) variant", v, r, flush=True)
+    lib.ga_set_tuning(4, 0)
     r = timeit(lambda: lib.ga_nn_distance_bwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(g1.data_ptr()),
                                               p(i1.data_ptr()), p(g2.data_ptr()), p(i2.data_ptr()),
                                               p(o1.data_ptr()), p(o2.data_ptr()), p(st)))
