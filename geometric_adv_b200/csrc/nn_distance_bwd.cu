@@ -77,13 +77,30 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
       uint32_t* z = reinterpret_cast<uint32_t*>(cnt);
       for (int i = tid; i < W * K / 2; i += kBwdThreads) z[i] = 0u;
     }
+    // keys of this warp's first chunks, loaded together (one global latency instead of one per
+    // chunk; covers the whole segment for clouds up to 2048 points)
+    constexpr int KPRE = 4;
+    int kpre[KPRE];
+#pragma unroll
+    for (int c = 0; c < KPRE; c++) {
+      const int e = e_begin + c * 32 + lane;
+      kpre[c] = e < e_end ? __ldg(oth_idx + e) : -1;
+    }
     __syncthreads();
     // 2. per-warp histogram of its contiguous element segment
-    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+    for (int e0 = e_begin, c = 0; e0 < e_end; e0 += 32, c++) {
       const int e = e0 + lane;
       int key = -1 - lane;
       if (e < e_end) {
-        const int kk = __ldg(oth_idx + e) - k0;
+        int raw;
+        if (c < KPRE) {
+          raw = kpre[0];
+#pragma unroll
+          for (int q = 1; q < KPRE; q++) raw = c == q ? kpre[q] : raw;
+        } else {
+          raw = __ldg(oth_idx + e);
+        }
+        const int kk = raw - k0;
         if (kk >= 0 && kk < kn) key = kk;
       }
       const unsigned mask = __match_any_sync(0xffffffffu, key);
@@ -129,11 +146,19 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
     }
     __syncthreads();
     // 5. stable placement: same walk as step 2, ranks within a warp chunk from match.any
-    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+    for (int e0 = e_begin, c = 0; e0 < e_end; e0 += 32, c++) {
       const int e = e0 + lane;
       int key = -1 - lane;
       if (e < e_end) {
-        const int kk = __ldg(oth_idx + e) - k0;
+        int raw;
+        if (c < KPRE) {
+          raw = kpre[0];
+#pragma unroll
+          for (int q = 1; q < KPRE; q++) raw = c == q ? kpre[q] : raw;
+        } else {
+          raw = __ldg(oth_idx + e);
+        }
+        const int kk = raw - k0;
         if (kk >= 0 && kk < kn) key = kk;
       }
       const unsigned mask = __match_any_sync(0xffffffffu, key);
@@ -147,47 +172,74 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
       __syncwarp();
     }
     __syncthreads();
-    // 6. one thread per output point, contributors in ascending order
-    for (int k = tid; k < kn; k += kBwdThreads) {
-      const int p = k0 + k;
-      const float ox = __ldg(own + (size_t)p * 3), oy = __ldg(own + (size_t)p * 3 + 1),
-                  oz = __ldg(own + (size_t)p * 3 + 2);
-      // direct term (own loop of the reference)
-      float dx = 0.f, dy = 0.f, dz = 0.f;
-      {
-        const int j2 = __ldg(own_idx + p);
-        if (j2 >= 0 && j2 < L) {
-          const float g = __fmul_rn(__ldg(own_gd + p), 2.0f);
-          dx = __fmul_rn(g, __fsub_rn(ox, __ldg(oth + (size_t)j2 * 3)));
-          dy = __fmul_rn(g, __fsub_rn(oy, __ldg(oth + (size_t)j2 * 3 + 1)));
-          dz = __fmul_rn(g, __fsub_rn(oz, __ldg(oth + (size_t)j2 * 3 + 2)));
+    // 6. one thread per output point (PER points per thread, handled together so that the
+    //    independent global loads of all of them are in flight at once); contributors of each
+    //    point are subtracted in ascending order
+    {
+      constexpr int PER = K / kBwdThreads;
+      float ox[PER], oy[PER], oz[PER], gown[PER];
+      int j2[PER], s0[PER], cn[PER];
+      bool ok[PER];
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        const int k = tid + i * kBwdThreads;
+        ok[i] = k < kn;
+        const int p = k0 + (ok[i] ? k : 0);
+        ox[i] = __ldg(own + (size_t)p * 3);
+        oy[i] = __ldg(own + (size_t)p * 3 + 1);
+        oz[i] = __ldg(own + (size_t)p * 3 + 2);
+        j2[i] = __ldg(own_idx + p);
+        gown[i] = __ldg(own_gd + p);
+        s0[i] = ok[i] ? start[k] : 0;
+        cn[i] = ok[i] ? total[k] : 0;
+      }
+      float dx[PER], dy[PER], dz[PER], ax[PER], ay[PER], az[PER];
+      int maxc = 0;
+#pragma unroll
+      for (int i = 0; i < PER; i++) {  // direct term (own loop of the reference)
+        dx[i] = dy[i] = dz[i] = 0.f;
+        if (ok[i] && j2[i] >= 0 && j2[i] < L) {
+          const float g = __fmul_rn(gown[i], 2.0f);
+          dx[i] = __fmul_rn(g, __fsub_rn(ox[i], __ldg(oth + (size_t)j2[i] * 3)));
+          dy[i] = __fmul_rn(g, __fsub_rn(oy[i], __ldg(oth + (size_t)j2[i] * 3 + 1)));
+          dz[i] = __fmul_rn(g, __fsub_rn(oz[i], __ldg(oth + (size_t)j2[i] * 3 + 2)));
+        }
+        ax[i] = ay[i] = az[i] = 0.f;
+        if (side == 0) {  // loop 1 (direct) runs before loop 2 (scatter) for cloud 1
+          ax[i] = __fadd_rn(ax[i], dx[i]);
+          ay[i] = __fadd_rn(ay[i], dy[i]);
+          az[i] = __fadd_rn(az[i], dz[i]);
+        }
+        maxc = max(maxc, cn[i]);
+      }
+      for (int r = 0; r < maxc; r++) {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+          if (r < cn[i]) {
+            const int e = order[s0[i] + r];
+            const float g = __fmul_rn(__ldg(oth_gd + e), 2.0f);
+            const float tx = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3), ox[i]));
+            const float ty = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 1), oy[i]));
+            const float tz = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 2), oz[i]));
+            ax[i] = __fsub_rn(ax[i], tx);
+            ay[i] = __fsub_rn(ay[i], ty);
+            az[i] = __fsub_rn(az[i], tz);
+          }
         }
       }
-      float ax = 0.f, ay = 0.f, az = 0.f;
-      if (side == 0) {  // loop 1 (direct) runs before loop 2 (scatter) for cloud 1
-        ax = __fadd_rn(ax, dx);
-        ay = __fadd_rn(ay, dy);
-        az = __fadd_rn(az, dz);
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        if (!ok[i]) continue;
+        if (side == 1) {  // for cloud 2 the scatter of loop 1 comes first, its own loop 2 last
+          ax[i] = __fadd_rn(ax[i], dx[i]);
+          ay[i] = __fadd_rn(ay[i], dy[i]);
+          az[i] = __fadd_rn(az[i], dz[i]);
+        }
+        const int p = k0 + tid + i * kBwdThreads;
+        out[(size_t)p * 3] = ax[i];
+        out[(size_t)p * 3 + 1] = ay[i];
+        out[(size_t)p * 3 + 2] = az[i];
       }
-      const int s0 = start[k], s1 = s0 + total[k];
-      for (int s = s0; s < s1; s++) {
-        const int e = order[s];
-        const float g = __fmul_rn(__ldg(oth_gd + e), 2.0f);
-        const float tx = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3), ox));
-        const float ty = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 1), oy));
-        const float tz = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 2), oz));
-        ax = __fsub_rn(ax, tx);
-        ay = __fsub_rn(ay, ty);
-        az = __fsub_rn(az, tz);
-      }
-      if (side == 1) {  // for cloud 2 the scatter of loop 1 comes first, its own loop 2 last
-        ax = __fadd_rn(ax, dx);
-        ay = __fadd_rn(ay, dy);
-        az = __fadd_rn(az, dz);
-      }
-      out[(size_t)p * 3] = ax;
-      out[(size_t)p * 3 + 1] = ay;
-      out[(size_t)p * 3 + 2] = az;
     }
     __syncthreads();
   }

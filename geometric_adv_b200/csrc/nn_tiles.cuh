@@ -115,24 +115,33 @@ __device__ __forceinline__ void filter_scan(const float4* __restrict__ tgt, int 
   }
 }
 
-// Second scan for kNN: same pipelined walk as filter_scan, but every target whose
-// filter value is <= thr[j] is appended (chunk-local index, 16 bit) to query j's
-// queue.  Appends are predicated, not branched, so the warp stays in step; row
-// `cap` of the queue is a scratch row that absorbs writes after an overflow.
+// Second scan for kNN: same pipelined walk as filter_scan, but every target whose filter value
+// is <= thr[j] is appended (chunk-local index, 16 bit) to query j's queue.  Appends are
+// predicated stores through a running pointer (3-4 instructions per target, no branch, the warp
+// stays in step).  The queue has cap + T rows: a tile can add at most T entries, and the fill
+// level is checked once per tile; a query that passes `cap` stops collecting and reports
+// cnt = cap + 1 (overflow: the caller falls back to the exact warp path).
 template <int Q, int T>
 __device__ __forceinline__ void filter_collect(const float4* __restrict__ tgt, int ntile, const float (&ax2)[Q],
-                                               const float (&ay2)[Q], const float (&az2)[Q],
-                                               const float (&thr)[Q], int (&cnt)[Q],
-                                               unsigned short* __restrict__ queue, int qstride, int jstride,
-                                               int cap) {
+                                               const float (&ay2)[Q], const float (&az2)[Q], float (&thr)[Q],
+                                               int (&cnt)[Q], unsigned short* __restrict__ queue, int qstride,
+                                               int jstride, int cap) {
   constexpr int U = kPipeU;
   constexpr int NB = (T / 2) / U;
+  unsigned short* qp[Q];
+  bool over[Q];
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    qp[j] = queue + j * jstride;
+    over[j] = false;
+  }
   float4 buf[2][2 * U];
 #pragma unroll
   for (int e = 0; e < 2 * U; e++) buf[0][e] = tgt[e];
 #pragma unroll 1
   for (int tile = 0; tile < ntile; tile++) {
     const float4* tp = tgt + (size_t)tile * T;
+    const int gb = tile * T;
 #pragma unroll
     for (int blk = 0; blk < NB; blk++) {
 #pragma unroll
@@ -141,22 +150,31 @@ __device__ __forceinline__ void filter_collect(const float4* __restrict__ tgt, i
       for (int pp = 0; pp < U; pp++) {
         const float4 u = buf[blk & 1][2 * pp];
         const float4 v = buf[blk & 1][2 * pp + 1];
-        const int g = tile * T + (blk * U + pp) * 2;
 #pragma unroll
         for (int j = 0; j < Q; j++) {
           const float2 f = filter_pair(u, v, ax2[j], ay2[j], az2[j]);
           if (!(f.x > thr[j])) {  // NaN filter value / threshold counts as a candidate
-            queue[min(cnt[j], cap) * qstride + j * jstride] = (unsigned short)g;
-            cnt[j]++;
+            *qp[j] = (unsigned short)(gb + (blk * U + pp) * 2);
+            qp[j] += qstride;
           }
           if (!(f.y > thr[j])) {
-            queue[min(cnt[j], cap) * qstride + j * jstride] = (unsigned short)(g + 1);
-            cnt[j]++;
+            *qp[j] = (unsigned short)(gb + (blk * U + pp) * 2 + 1);
+            qp[j] += qstride;
           }
         }
       }
     }
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+      if ((int)(qp[j] - (queue + j * jstride)) > cap * qstride) {  // too many: stop collecting
+        over[j] = true;
+        qp[j] = queue + j * jstride;
+        thr[j] = -__int_as_float(0x7f800000);
+      }
+    }
   }
+#pragma unroll
+  for (int j = 0; j < Q; j++) cnt[j] = over[j] ? cap + 1 : (int)(qp[j] - (queue + j * jstride)) / qstride;
 }
 
 // Window of the filter (see nn_distance_fwd.cu): W = 128u (A+Bm)^2 + denormal slack.
