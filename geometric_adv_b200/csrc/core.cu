@@ -14,6 +14,8 @@ extern int g_knn_variant;  // grouping.cu
 extern int g_host_path;    // host_api.cu
 extern int g_host_chunks;  // host_api.cu
 extern int g_sorted_variant;  // nn_distance_sorted.cu
+extern int g_fwd_split;       // nn_distance_fwd.cu
+extern int g_fwd_split_q;     // nn_distance_fwd.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -98,6 +100,14 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 4) {
     ga::g_sorted_variant = value;
+    return GA_OK;
+  }
+  if (key == 5) {
+    ga::g_fwd_split = value;
+    return GA_OK;
+  }
+  if (key == 6) {
+    ga::g_fwd_split_q = value;
     return GA_OK;
   }
   ga::set_error("ga_set_tuning: unknown key %d", key);

@@ -25,6 +25,8 @@
 // degenerates to the plain reference scan (still exact).
 #include <atomic>
 
+#include <cooperative_groups.h>
+
 #include "nn_search.cuh"
 
 namespace ga {
@@ -93,6 +95,160 @@ __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_kernel(const FwdArgs a) 
   }
 }
 
+// ---- small problems: split the TARGETS of each query tile over a thread-block cluster ------
+// With few cloud pairs (B=1 per-cloud losses, autoencoder.py:150-168; the attack's batch of 10)
+// there are not enough query tiles to occupy 148 SMs.  Here a cluster of S CTAs shares one query
+// tile; CTA r stages and scans only tiles [r*tl, (r+1)*tl) of the target cloud.  Two exchanges
+// through distributed shared memory keep the result exact:
+//   1. every CTA publishes its filter minimum per query (and its max |coordinate|) to all others,
+//      so that all of them refine against the GLOBAL filter minimum and window;
+//   2. the exact partial results (value, index) go to rank 0, which merges them by
+//      (value, index) -- lowest index wins ties, as in the reference -- and writes the outputs.
+constexpr int kSplitMax = 8;
+using SplitCfg = FwdCfg<128, 2, 32, 2048>;   // tiny problems: most CTAs
+using SplitCfg4 = FwdCfg<128, 4, 32, 2048>;  // a few hundred query tiles: FMA-bound inner loop
+template <class Cfg>
+constexpr size_t split_smem() {
+  return Cfg::kSmem + (size_t)3 * kSplitMax * Cfg::kQT * 4 + kSplitMax * 4;
+}
+
+template <class Cfg, int MODE>
+__global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_split_kernel(const FwdArgs a, const int S) {
+  namespace cg = cooperative_groups;
+  constexpr int THREADS = Cfg::kThreads, Q = Cfg::kQ, QT = Cfg::kQT, T = Cfg::kT, CH = Cfg::kCH;
+  const float kInf = __int_as_float(0x7f800000);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ float4 smem_f4[];
+  float4* tgt = smem_f4;
+  float* red = reinterpret_cast<float*>(smem_f4 + CH + 2 * kPipeU);  // [32]
+  float* xf = red + 32;                                              // [kSplitMax][QT] filter minima
+  float* xb = xf + kSplitMax * QT;                                   // [kSplitMax][QT] exact partial values
+  int* xi = reinterpret_cast<int*>(xb + kSplitMax * QT);             // [kSplitMax][QT] exact partial indices
+  float* xbm = reinterpret_cast<float*>(xi + kSplitMax * QT);        // [kSplitMax] max |coordinate|
+
+  const int tid = threadIdx.x;
+  const int job = blockIdx.x / S;
+  const int jpb = a.tiles1 + a.tiles2;
+  const int batch = job / jpb;
+  const int r = job - batch * jpb;
+  const bool rev = r >= a.tiles1;
+  const int qtile = rev ? r - a.tiles1 : r;
+  const int nq = rev ? a.m : a.n;
+  const int nt = rev ? a.n : a.m;
+  const float* qpts = (rev ? a.xyz2 : a.xyz1) + (size_t)batch * nq * 3;
+  const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
+  float* odist = (rev ? a.dist2 : a.dist1) + (size_t)batch * nq;
+  int* oidx = (rev ? a.idx2 : a.idx1) + (size_t)batch * nq;
+
+  const int ntile_all = (nt + T - 1) / T;
+  const int tl = (ntile_all + S - 1) / S;
+  const int tile0 = min(ntile_all, rank * tl);
+  const int ntl = min(tl, ntile_all - tile0);
+  const int c0 = tile0 * T;
+
+  QueryState<Q> s;
+  load_queries<Cfg, MODE>(s, qpts, nq, qtile, tpts, tid);
+  const float bm = stage_targets<THREADS, T>(tgt, red, tpts, c0, nt, ntl, tid);
+  TileTrack<Q> tr;
+  search_phase1<Cfg>(s, tgt, ntl, tr);
+
+  for (int rr = 0; rr < S; rr++) {  // publish this CTA's filter minima to every CTA of the cluster
+    float* dst = cluster.map_shared_rank(xf, rr);
+#pragma unroll
+    for (int j = 0; j < Q; j++) dst[rank * QT + j * THREADS + tid] = tr.c1[j];
+    if (tid == 0) cluster.map_shared_rank(xbm, rr)[rank] = bm;
+  }
+  cluster.sync();
+  float fmin[Q];
+  float bmg = 0.0f;
+#pragma unroll
+  for (int j = 0; j < Q; j++) fmin[j] = kInf;
+  for (int rr = 0; rr < S; rr++) {
+#pragma unroll
+    for (int j = 0; j < Q; j++) fmin[j] = fminf(fmin[j], xf[rr * QT + j * THREADS + tid]);
+    bmg = fmaxf(bmg, xbm[rr]);
+  }
+  search_phase2<Cfg, MODE>(s, tgt, c0, nt, ntl, tr, fmin, bmg);
+
+  {
+    float* b0 = cluster.map_shared_rank(xb, 0);
+    int* i0 = cluster.map_shared_rank(xi, 0);
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+      b0[rank * QT + j * THREADS + tid] = s.best[j];
+      i0[rank * QT + j * THREADS + tid] = s.besti[j];
+    }
+  }
+  cluster.sync();
+  if (rank != 0) return;
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    if (!s.valid[j]) continue;
+    float b = kInf;
+    int bi = 0;
+    for (int rr = 0; rr < S; rr++) {
+      const float ob = xb[rr * QT + j * THREADS + tid];
+      const int obi = xi[rr * QT + j * THREADS + tid];
+      if (ob < b || (ob == b && obi < bi && ob < kInf)) {
+        b = ob;
+        bi = obi;
+      }
+    }
+    s.best[j] = b;
+    s.besti[j] = bi;
+    const int qi = qtile * QT + j * THREADS + tid;
+    float d;
+    int i;
+    finish_query<Q>(s, j, d, i);
+    odist[qi] = d;
+    oidx[qi] = i;
+    float* mdist = rev ? a.mdist2 : a.mdist1;
+    int* midx = rev ? a.midx2 : a.midx1;
+    if (mdist != nullptr) {
+      mdist[(size_t)batch * nq + qi] = d;
+      midx[(size_t)batch * nq + qi] = i;
+    }
+  }
+}
+
+template <class Cfg>
+static int launch_fwd_split(FwdArgs a, int mode, int S, cudaStream_t st) {
+  constexpr size_t kSplitSmem = split_smem<Cfg>();
+  a.tiles1 = (a.n + Cfg::kQT - 1) / Cfg::kQT;
+  a.tiles2 = (a.m + Cfg::kQT - 1) / Cfg::kQT;
+  const long long jobs = (long long)a.b * (a.tiles1 + a.tiles2);
+  auto k = mode == GA_MODE_CPU_EXACT ? nn_fwd_split_kernel<Cfg, GA_MODE_CPU_EXACT>
+                                     : nn_fwd_split_kernel<Cfg, GA_MODE_GPU_REF>;
+  {
+    static std::atomic<unsigned> done_mask[2];
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done_mask[mode].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplitSmem));
+      done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(jobs * S));
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = kSplitSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GA_CUDA_TRY(cudaLaunchKernelEx(&cfg, k, a, S));
+  GA_LAUNCH_CHECK("nn_fwd_split_kernel");
+  return GA_OK;
+}
+
+int g_fwd_split = -1;    // tuning hook (key 5): -1 auto, 0 never, 2/4/8 force
+int g_fwd_split_q = 0;   // tuning hook (key 6): 0 auto, 2 or 4 queries per thread in the split kernel
+
 template <class Cfg>
 static int launch_fwd(const FwdArgs& a, int mode, cudaStream_t st) {
   const long long jobs = (long long)a.b * (a.tiles1 + a.tiles2);
@@ -155,6 +311,23 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   // Default: 4 queries per thread (FMA-pipe bound scan).  Small problems (few hundred query
   // tiles, e.g. the B=1 calls of autoencoder.py:150-168) take 2 queries per thread instead:
   // twice the CTAs to spread over the 148 SMs matters more than the LDS-bound inner loop.
+  // Few query tiles and clouds that fit one chunk: split the targets over a cluster.
+  if (n <= SplitCfg::kCH && m <= SplitCfg::kCH && g_fwd_variant == 0 && g_fwd_split != 0) {
+    const long long jobs2 = (long long)b * ((n + SplitCfg::kQT - 1) / SplitCfg::kQT + (m + SplitCfg::kQT - 1) / SplitCfg::kQT);
+    const long long jobs4 = (long long)b * ((n + SplitCfg4::kQT - 1) / SplitCfg4::kQT + (m + SplitCfg4::kQT - 1) / SplitCfg4::kQT);
+    const int mintiles = ((n < m ? n : m) + SplitCfg::kT - 1) / SplitCfg::kT;
+    // measured (profiles/r01_tune.json): 2 queries per thread wins at B=1 (12.2 vs 15.2 us) and
+    // B=10 (30.7 vs 32.8 us); 4 per thread is kept selectable for tuning
+    const bool q4 = g_fwd_split_q == 4;
+    const long long jobs = q4 ? jobs4 : jobs2;
+    int S = 1;
+    if (g_fwd_split > 0) {
+      S = g_fwd_split;
+    } else {
+      while (S < kSplitMax && jobs * S * 2 <= 148 * 4 && mintiles / (S * 2) >= 4) S *= 2;
+    }
+    if (S > 1) return q4 ? launch_fwd_split<SplitCfg4>(a, mode, S, st) : launch_fwd_split<SplitCfg>(a, mode, S, st);
+  }
   int variant = g_fwd_variant;
   if (variant == 0) {
     const long long queries = (long long)b * ((long long)n + m);

@@ -138,52 +138,62 @@ __device__ __forceinline__ void load_queries(QueryState<Cfg::kQ>& s, const float
   }
 }
 
-// Search one staged chunk (targets [c0, c0 + ntile*T) of a cloud with nt points).
-// bm_run: max |coordinate| over all targets staged so far (including this chunk).
-// Must be called by whole, converged warps (it uses warp collectives).
-template <class Cfg, int MODE>
-__device__ __forceinline__ void search_chunk(QueryState<Cfg::kQ>& s, const float4* __restrict__ tgt, int c0, int nt,
-                                             int ntile, float bm_run) {
-  constexpr int Q = Cfg::kQ, T = Cfg::kT;
-  const float kInf = __int_as_float(0x7f800000);
-  // ---- phase 1: filter scan; three smallest tile minima per query ----------
+// The three smallest tile minima of the filter per query, and the tiles of the two smallest.
+template <int Q>
+struct TileTrack {
   float c1[Q], c2[Q], c3[Q];
   int i1[Q], i2[Q];
+};
+
+// Phase 1: filter scan over the `ntile` staged tiles; per query the three smallest tile minima.
+template <class Cfg>
+__device__ __forceinline__ void search_phase1(const QueryState<Cfg::kQ>& s, const float4* __restrict__ tgt,
+                                              int ntile, TileTrack<Cfg::kQ>& tr) {
+  constexpr int Q = Cfg::kQ, T = Cfg::kT;
+  const float kInf = __int_as_float(0x7f800000);
 #pragma unroll
   for (int j = 0; j < Q; j++) {
-    c1[j] = c2[j] = c3[j] = kInf;
-    i1[j] = i2[j] = 0;
+    tr.c1[j] = tr.c2[j] = tr.c3[j] = kInf;
+    tr.i1[j] = tr.i2[j] = 0;
   }
   filter_scan<Q, T>(tgt, ntile, s.ax2, s.ay2, s.az2, [&](int tile, const float(&tm)[Q]) {
 #pragma unroll
     for (int j = 0; j < Q; j++) {
-      const bool lt1 = tm[j] < c1[j], lt2 = tm[j] < c2[j];
-      c3[j] = fminf(c3[j], fmaxf(c2[j], tm[j]));
-      i2[j] = lt1 ? i1[j] : (lt2 ? tile : i2[j]);
-      c2[j] = fminf(c2[j], fmaxf(c1[j], tm[j]));
-      i1[j] = lt1 ? tile : i1[j];
-      c1[j] = fminf(c1[j], tm[j]);
+      const bool lt1 = tm[j] < tr.c1[j], lt2 = tm[j] < tr.c2[j];
+      tr.c3[j] = fminf(tr.c3[j], fmaxf(tr.c2[j], tm[j]));
+      tr.i2[j] = lt1 ? tr.i1[j] : (lt2 ? tile : tr.i2[j]);
+      tr.c2[j] = fminf(tr.c2[j], fmaxf(tr.c1[j], tm[j]));
+      tr.i1[j] = lt1 ? tile : tr.i1[j];
+      tr.c1[j] = fminf(tr.c1[j], tm[j]);
     }
   });
+}
 
-  // ---- phase 2: refine the qualifying tiles in the reference arithmetic -----
+// Phase 2: refine the staged tiles whose minimum is within the window of fmin[j] (the smallest
+// filter value of query j over ALL targets examined so far, possibly by other CTAs) in the
+// reference arithmetic.  c0 = index of the first staged target in its cloud (nt points).
+// Must be called by whole, converged warps (it uses warp collectives).
+template <class Cfg, int MODE>
+__device__ __forceinline__ void search_phase2(QueryState<Cfg::kQ>& s, const float4* __restrict__ tgt, int c0, int nt,
+                                              int ntile, const TileTrack<Cfg::kQ>& tr, const float (&fmin)[Cfg::kQ],
+                                              float bm_run) {
+  constexpr int Q = Cfg::kQ, T = Cfg::kT;
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < Q; j++) {
     float thr = 0.0f;
     bool hard = false;  // needs the cooperative scan
     if (s.valid[j]) {
-      s.m1g[j] = fminf(s.m1g[j], c1[j]);
-      thr = s.m1g[j] + filter_window(s.qabs[j], bm_run);
-      hard = !(c3[j] > thr);  // three or more tiles in the window, or non-finite data
+      thr = fmin[j] + filter_window(s.qabs[j], bm_run);
+      hard = !(tr.c3[j] > thr);  // three or more tiles in the window, or non-finite data
       if (!hard) {
         int cnt = 0, ca = 0, cb = 0;
-        if (!(c1[j] > thr))
-          scan_tile_candidates<T>(tgt + (size_t)i1[j] * T, c0 + i1[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
-                                  cnt, ca, cb);
-        if (!(c2[j] > thr))
-          scan_tile_candidates<T>(tgt + (size_t)i2[j] * T, c0 + i2[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr,
-                                  cnt, ca, cb);
+        if (!(tr.c1[j] > thr))
+          scan_tile_candidates<T>(tgt + (size_t)tr.i1[j] * T, c0 + tr.i1[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j],
+                                  thr, cnt, ca, cb);
+        if (!(tr.c2[j] > thr))
+          scan_tile_candidates<T>(tgt + (size_t)tr.i2[j] * T, c0 + tr.i2[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j],
+                                  thr, cnt, ca, cb);
         // the usual case: one or two survivors, evaluated by all lanes in step
         if (cnt >= 1 && cnt <= 2) eval_candidate<MODE>(tgt, c0, ca, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
         if (cnt == 2) eval_candidate<MODE>(tgt, c0, cb, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
@@ -209,6 +219,19 @@ __device__ __forceinline__ void search_chunk(QueryState<Cfg::kQ>& s, const float
       }
     }
   }
+}
+
+// Search one staged chunk (targets [c0, c0 + ntile*T) of a cloud with nt points).
+// bm_run: max |coordinate| over all targets staged so far (including this chunk).
+template <class Cfg, int MODE>
+__device__ __forceinline__ void search_chunk(QueryState<Cfg::kQ>& s, const float4* __restrict__ tgt, int c0, int nt,
+                                             int ntile, float bm_run) {
+  constexpr int Q = Cfg::kQ;
+  TileTrack<Q> tr;
+  search_phase1<Cfg>(s, tgt, ntile, tr);
+#pragma unroll
+  for (int j = 0; j < Q; j++) s.m1g[j] = fminf(s.m1g[j], tr.c1[j]);
+  search_phase2<Cfg, MODE>(s, tgt, c0, nt, ntile, tr, s.m1g, bm_run);
 }
 
 // Final (dist, idx) of query slot j with the reference's NaN-seed rule.

@@ -27,20 +27,29 @@ def run_fwd(ga, a, b, mode=0):
 
 
 def check_fwd(ga, oracle, a, b, mode=0):
-    """Both forward paths (plain scan, and Morton-ordered scan with tile skipping) against the oracle."""
+    """Every forward path against the oracle: the plain scan, the Morton-ordered scan with tile
+    skipping, and the cluster kernel that splits the targets over 2 / 8 CTAs (forced here; the
+    library picks it by itself for small batches)."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
     want = oracle.nn_distance(a, b, mode)
     names = ["dist1", "idx1", "dist2", "idx2"]
     got = None
-    for pruning in (False, True):
+    variants = [("plain", False, 0), ("pruned", True, 0)]
+    if 0 < a.shape[1] <= 2048 and 0 < b.shape[1] <= 2048:
+        variants += [("split2", False, 2), ("split8", False, 8)]
+    for name, pruning, split in variants:
         ga.set_pruning(pruning)
+        lib.ga_set_tuning(5, split)
         try:
             got = run_fwd(ga, a, b, mode)
         finally:
             ga.set_pruning(False)
+            lib.ga_set_tuning(5, -1)
         for nme, g, w in zip(names, got, want):
-            assert bits_equal(g, w), "%s differs (shape %s vs %s, mode %d, pruning %s): %d mismatches" % (
-                nme, a.shape, b.shape, mode, pruning, int(np.sum(g != w)))
-    return got
+            assert bits_equal(g, w), "%s differs (shape %s vs %s, mode %d, path %s): %d mismatches" % (
+                nme, a.shape, b.shape, mode, name, int(np.sum(g != w)))
+    return run_fwd(ga, a, b, mode)
 
 
 # ------------------------------------------------------------------ forward

@@ -77,6 +77,16 @@ for (b, n, m) in [(50, 2048, 2048), (10, 2048, 2048), (1, 2048, 2048), (512, 204
     r = timeit(lambda: lib.ga_nn_distance_fwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()),
                                               p(i1.data_ptr()), p(d2.data_ptr()), p(i2.data_ptr()), 1, p(st)))
     out[key]["variant0_mode1"] = r
+    if b <= 50:
+        for qq in (2, 4):
+            for S in (1, 2, 4, 8):
+                lib.ga_set_tuning(5, S if S > 1 else 0); lib.ga_set_tuning(6, qq)
+                r = timeit(lambda: lib.ga_nn_distance_fwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()),
+                                                          p(d1.data_ptr()), p(i1.data_ptr()), p(d2.data_ptr()),
+                                                          p(i2.data_ptr()), 0, p(st)))
+                out[key]["split_q%d_S%d" % (qq, S)] = r
+                print(key, "split q", qq, "S", S, r, flush=True)
+        lib.ga_set_tuning(5, -1); lib.ga_set_tuning(6, 0)
     wsb = lib.ga_nn_distance_workspace_bytes(b, n, m)
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
     for v in range(5):
