@@ -16,6 +16,7 @@ extern int g_host_chunks;  // host_api.cu
 extern int g_sorted_variant;  // nn_distance_sorted.cu
 extern int g_fwd_split;       // nn_distance_fwd.cu
 extern int g_fwd_split_q;     // nn_distance_fwd.cu
+extern int g_mma_cfg;         // nn_distance_fwd_mma.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -108,6 +109,10 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 6) {
     ga::g_fwd_split_q = value;
+    return GA_OK;
+  }
+  if (key == 7) {
+    ga::g_mma_cfg = value;
     return GA_OK;
   }
   ga::set_error("ga_set_tuning: unknown key %d", key);

@@ -31,22 +31,6 @@
 
 namespace ga {
 
-struct FwdArgs {
-  int b, n, m;
-  const float* xyz1;
-  const float* xyz2;
-  float* dist1;
-  int* idx1;
-  float* dist2;
-  int* idx2;
-  int tiles1, tiles2;  // query tiles per cloud, direction 1->2 and 2->1
-  // optional second destination for every output (mapped pinned HOST memory: the host entry
-  // points let the kernel stream results over PCIe while it computes, instead of a D2H copy)
-  float* mdist1;
-  int* midx1;
-  float* mdist2;
-  int* midx2;
-};
 
 template <class Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_kernel(const FwdArgs a) {
@@ -275,6 +259,7 @@ static int launch_fwd(const FwdArgs& a, int mode, cudaStream_t st) {
 }
 
 int g_fwd_variant = 0;  // tuning hook (ga_set_tuning): 0 = default
+int launch_fwd_mma(const FwdArgs& a, int mode, cudaStream_t st);  // nn_distance_fwd_mma.cu
 
 }  // namespace ga
 
@@ -333,6 +318,7 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
     const long long queries = (long long)b * ((long long)n + m);
     variant = queries < 148LL * 2 * 512 ? 4 : 1;
   }
+  if (variant == 20) return launch_fwd_mma(a, mode, st);
   switch (variant) {
 #define GA_FWD_CASE(ID, TH, QQ, TT, CC)                                                          \
   case ID: {                                                                                     \

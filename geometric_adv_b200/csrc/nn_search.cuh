@@ -7,6 +7,24 @@
 
 namespace ga {
 
+// Arguments of every Chamfer forward kernel (nn_distance_fwd.cu, nn_distance_fwd_mma.cu).
+struct FwdArgs {
+  int b, n, m;
+  const float* xyz1;
+  const float* xyz2;
+  float* dist1;
+  int* idx1;
+  float* dist2;
+  int* idx2;
+  int tiles1, tiles2;  // query tiles per cloud, direction 1->2 and 2->1
+  // optional second destination for every output (mapped pinned HOST memory: the host entry
+  // points let the kernel stream results over PCIe while it computes, instead of a D2H copy)
+  float* mdist1;
+  int* midx1;
+  float* mdist2;
+  int* midx2;
+};
+
 template <int THREADS, int Q, int T, int CH>
 struct FwdCfg {
   static constexpr int kThreads = THREADS;

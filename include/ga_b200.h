@@ -170,6 +170,10 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
 int ga_set_tuning(int key, int value);
 /* Empty-kernel launch floor in microseconds (average over `reps` launches). */
 int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);
+/* Evidence for the tensor-core filter (forward variant 20, nn_mma.cuh): the raw filter values
+ * h(q,t) ~ |t|^2 - 2 q.t of one cloud pair, out[q*m + t], n queries (xyz1), m <= 2048 targets
+ * (xyz2), device pointers.  Tests compare it with the fp64 value against the documented bound. */
+int ga_debug_mma_filter(int n, int m, const float* xyz1, const float* xyz2, float* out, ga_stream_t stream);
 
 #ifdef __cplusplus
 }

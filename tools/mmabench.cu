@@ -1,0 +1,130 @@
+// Microbenchmark for the tensor-core filter of nn_fwd_mma_kernel: issue rate of the
+// legacy warp-level HMMA (mma.sync.m16n8k16 bf16 -> f32) on sm_100a, alone and together
+// with the FMNMX3 reduction and the LDS.64 B-fragment loads of the real inner loop.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mmabench.bin mmabench.cu
+// Output: one line per (kernel, warps per SM) with SM cycles per n-tile step per warp and
+// the resulting filter evaluations per clock per SM (one step = 4 MMAs = 64 queries x 8 targets).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CK(x)                                                                   \
+  do {                                                                          \
+    cudaError_t e = (x);                                                        \
+    if (e != cudaSuccess) {                                                     \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+      exit(1);                                                                  \
+    }                                                                           \
+  } while (0)
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
+                                         const float (&z)[4]) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(z[0]), "f"(z[1]), "f"(z[2]), "f"(z[3]));
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// MODE 0: chained accumulators (c += a*b), no reduction: pure HMMA rate with MT independent chains
+// MODE 1: zero C, B from shared memory, 2 FMNMX3 per MMA (the real inner loop)
+// MODE 2: as 1 without the FMNMX3 (results folded with one add per MMA to keep them alive)
+// MODE 3: as 1 with B kept in registers (no LDS)
+template <int MODE, int MT>
+__global__ void __launch_bounds__(256) bench(float* out, int steps, long long* cyc) {
+  __shared__ uint2 bfrag[64 * 32];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) bfrag[i] = make_uint2(0x3f803f80u + i, 0x3f803f80u);
+  __syncthreads();
+  uint32_t a[MT][4];
+#pragma unroll
+  for (int i = 0; i < MT; i++)
+#pragma unroll
+    for (int r = 0; r < 4; r++) a[i][r] = 0x3f803f80u + lane + i * 7 + r;
+  float c[MT][4];
+  float rm[MT][2];
+  const float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < MT; i++) {
+    rm[i][0] = rm[i][1] = 1e30f;
+#pragma unroll
+    for (int r = 0; r < 4; r++) c[i][r] = 0.f;
+  }
+  const long long t0 = clock64();
+  uint2 bf = bfrag[lane];
+#pragma unroll 4
+  for (int s = 0; s < steps; s++) {
+    if (MODE == 1 || MODE == 2) bf = bfrag[(s & 63) * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+      if (MODE == 0) {
+        mma16816(c[i], a[i], bf.x, bf.y, c[i]);
+      } else {
+        mma16816(c[i], a[i], bf.x, bf.y, z);
+        if (MODE == 1 || MODE == 3) {
+          rm[i][0] = fmin3(rm[i][0], c[i][0], c[i][1]);
+          rm[i][1] = fmin3(rm[i][1], c[i][2], c[i][3]);
+        } else {
+          rm[i][0] += c[i][0];
+        }
+      }
+    }
+    if (MODE == 3) bf.x += 1;
+  }
+  const long long t1 = clock64();
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < MT; i++) acc += rm[i][0] + rm[i][1] + c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (acc == 123.456f) out[0] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+template <int MODE, int MT>
+static void run(const char* name, int warps_per_sm, int sms) {
+  float* out;
+  long long* cyc;
+  CK(cudaMalloc(&out, 4));
+  CK(cudaMalloc(&cyc, 8));
+  const int steps = 1 << 14;
+  const int threads = warps_per_sm >= 8 ? 256 : warps_per_sm * 32;
+  const int ctas_per_sm = warps_per_sm * 32 / threads;
+  bench<MODE, MT><<<sms * ctas_per_sm, threads>>>(out, steps, cyc);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  bench<MODE, MT><<<sms * ctas_per_sm, threads>>>(out, steps, cyc);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  long long h = 0;
+  CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+  const double clk_per_step_warp = (double)h / steps;                    // one warp's view
+  const double clk_per_step_sm = clk_per_step_warp / warps_per_sm;       // SM cycles per warp-step
+  const double evals_per_clk_sm = (double)MT * 128.0 / clk_per_step_sm;  // 16x8 outputs per MMA
+  const double mma_per_clk_sm = (double)MT / clk_per_step_sm;
+  printf("%-28s MT=%d warps/SM=%2d  %.2f ms  clk/step/warp=%7.2f  MMA/clk/SM=%.3f  evals/clk/SM=%.1f\n", name, MT,
+         warps_per_sm, ms, clk_per_step_warp, mma_per_clk_sm, evals_per_clk_sm);
+  cudaFree(out);
+  cudaFree(cyc);
+}
+
+int main() {
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, 0));
+  printf("device %s, %d SMs\n", p.name, p.multiProcessorCount);
+  const int sms = p.multiProcessorCount;
+  for (int w : {4, 8, 16}) run<0, 4>("hmma chained", w, sms);
+  for (int w : {4, 8, 16}) run<0, 8>("hmma chained", w, sms);
+  for (int w : {4, 8, 16}) run<2, 4>("hmma zeroC + lds", w, sms);
+  for (int w : {4, 8, 16}) run<3, 4>("hmma zeroC + 2 fmnmx3 (regs)", w, sms);
+  for (int w : {4, 8, 16}) run<1, 4>("hmma zeroC + lds + 2 fmnmx3", w, sms);
+  for (int w : {4, 8, 16}) run<1, 2>("hmma zeroC + lds + 2 fmnmx3", w, sms);
+  return 0;
+}
