@@ -17,6 +17,7 @@ extern int g_sorted_variant;  // nn_distance_sorted.cu
 extern int g_fwd_split;       // nn_distance_fwd.cu
 extern int g_fwd_split_q;     // nn_distance_fwd.cu
 extern int g_mma_cfg;         // nn_distance_fwd_mma.cu
+extern int g_mma_grid;        // nn_distance_fwd_mma.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -113,6 +114,10 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 7) {
     ga::g_mma_cfg = value;
+    return GA_OK;
+  }
+  if (key == 8) {
+    ga::g_mma_grid = value;
     return GA_OK;
   }
   ga::set_error("ga_set_tuning: unknown key %d", key);

@@ -259,7 +259,8 @@ static int launch_fwd(const FwdArgs& a, int mode, cudaStream_t st) {
 }
 
 int g_fwd_variant = 0;  // tuning hook (ga_set_tuning): 0 = default
-int launch_fwd_mma(const FwdArgs& a, int mode, cudaStream_t st);  // nn_distance_fwd_mma.cu
+int launch_fwd_mma(const FwdArgs& a, int mode, cudaStream_t st);          // nn_distance_fwd_mma.cu
+int launch_fwd_mma_persist(const FwdArgs& a, int mode, cudaStream_t st);  // nn_distance_fwd_mma.cu
 
 }  // namespace ga
 
@@ -296,8 +297,13 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   // Default: 4 queries per thread (FMA-pipe bound scan).  Small problems (few hundred query
   // tiles, e.g. the B=1 calls of autoencoder.py:150-168) take 2 queries per thread instead:
   // twice the CTAs to spread over the 148 SMs matters more than the LDS-bound inner loop.
+  // Batches that give the tensor-core kernel at least half a wave of 512-query CTAs take it
+  // (measured, profiles/r01_tune_mma.json: B=50 56 vs 78 us, B=512 401 vs 612 us, B=10 27.7 vs
+  // 30.7 us, 4 x 8192 points 84 vs 113 us); below that the fp32-filter kernels win.
+  const bool mma_auto = g_fwd_variant == 0 && g_fwd_split <= 0 && n >= 256 && m >= 256 &&
+                        (long long)b * ((n + 511) / 512 + (m + 511) / 512) >= 74;
   // Few query tiles and clouds that fit one chunk: split the targets over a cluster.
-  if (n <= SplitCfg::kCH && m <= SplitCfg::kCH && g_fwd_variant == 0 && g_fwd_split != 0) {
+  if (!mma_auto && n <= SplitCfg::kCH && m <= SplitCfg::kCH && g_fwd_variant == 0 && g_fwd_split != 0) {
     const long long jobs2 = (long long)b * ((n + SplitCfg::kQT - 1) / SplitCfg::kQT + (m + SplitCfg::kQT - 1) / SplitCfg::kQT);
     const long long jobs4 = (long long)b * ((n + SplitCfg4::kQT - 1) / SplitCfg4::kQT + (m + SplitCfg4::kQT - 1) / SplitCfg4::kQT);
     const int mintiles = ((n < m ? n : m) + SplitCfg::kT - 1) / SplitCfg::kT;
@@ -316,9 +322,10 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   int variant = g_fwd_variant;
   if (variant == 0) {
     const long long queries = (long long)b * ((long long)n + m);
-    variant = queries < 148LL * 2 * 512 ? 4 : 1;
+    variant = mma_auto ? 20 : (queries < 148LL * 2 * 512 ? 4 : 1);
   }
   if (variant == 20) return launch_fwd_mma(a, mode, st);
+  if (variant == 21) return launch_fwd_mma_persist(a, mode, st);
   switch (variant) {
 #define GA_FWD_CASE(ID, TH, QQ, TT, CC)                                                          \
   case ID: {                                                                                     \

@@ -23,7 +23,7 @@ struct MmaCfg {
   static constexpr int kThreads = WARPS * 32;
   static constexpr int kQT = WARPS * kMmaQW;  // queries per CTA
   static constexpr int kCH = CH;              // targets staged per chunk
-  static_assert(CH % kMmaBlk == 0, "chunk must hold whole MMA blocks");
+  static_assert(CH % kMmaBlk == 0 && CH / kMmaBlk <= 16, "whole MMA blocks, block number must fit 4 key bits");
   // pair-SoA (+pipeline pad) | red[32] | B fragments | per-query tile lists (count, 2 tiles)
   static constexpr size_t kOffRed = (size_t)CH * 16 + (size_t)kPipeU * 32;
   static constexpr size_t kOffB = kOffRed + 32 * 4;
@@ -31,6 +31,109 @@ struct MmaCfg {
   static constexpr size_t kOffTile = kOffCnt + (size_t)kQT * 4;
   static constexpr size_t kSmem = kOffTile + (size_t)kQT * 4;
 };
+
+// The two queries a lane refines and writes: m-tile t = lane&3, rows g = lane>>2 and g+8 of the
+// warp's 64 queries, i.e. local queries 16 t + g + 8 j.
+template <int MODE>
+__device__ __forceinline__ void mma_init_queries(QueryState<2>& s, const float* __restrict__ qpts, int nq, int qbase,
+                                                 const float* __restrict__ tpts, int lane) {
+  const float kInf = __int_as_float(0x7f800000);
+  const int g = lane >> 2, t = lane & 3;
+  const float t0x = __ldg(tpts), t0y = __ldg(tpts + 1), t0z = __ldg(tpts + 2);
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int qi = qbase + 16 * t + g + 8 * j;
+    s.valid[j] = qi < nq;
+    const int qs = s.valid[j] ? qi : 0;
+    s.qx[j] = __ldg(qpts + (size_t)qs * 3);
+    s.qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
+    s.qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
+    s.qabs[j] = query_abs(s.qx[j], s.qy[j], s.qz[j]);
+    s.ax2[j] = -2.0f * s.qx[j];
+    s.ay2[j] = -2.0f * s.qy[j];
+    s.az2[j] = -2.0f * s.qz[j];
+    s.d0[j] = sqdist<MODE>(t0x, t0y, t0z, s.qx[j], s.qy[j], s.qz[j]);
+    s.best[j] = kInf;
+    s.besti[j] = 0;
+    s.m1g[j] = kInf;
+  }
+}
+
+// One staged chunk (targets [c0, c0 + cn) of a cloud with nt points) for one warp: tensor-core
+// scan, per-query lists of the qualifying tiles, exact refine.  mrun: running row minima of h over
+// the chunks seen so far (same value in the 4 lanes of a quad); wcnt / wtile: this warp's lists.
+template <int MODE>
+__device__ __forceinline__ void mma_chunk(const MmaRows& R, QueryState<2>& s, float (&mrun)[8],
+                                          const float4* __restrict__ tgt, const uint4* __restrict__ bfrag, int c0, int nt,
+                                          int cn, float bm_run, int* __restrict__ wcnt,
+                                          unsigned short* __restrict__ wtile, int lane) {
+  constexpr int T = kMmaT;
+  const int g = lane >> 2, t = lane & 3;
+  const int ntile = (cn + T - 1) / T;
+  const int nblk = (cn + kMmaBlk - 1) / kMmaBlk;
+  wcnt[16 * t + g] = 0;
+  wcnt[16 * t + g + 8] = 0;
+  __syncwarp();
+
+  MmaTrack tr;
+  mma_scan(R, reinterpret_cast<const uint2*>(bfrag), nblk, lane, tr);
+
+  // Row minimum over the quad, window, and the qualifying tiles of this lane -> per-query lists.
+  float mythr[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    float m = tr.c1[r];
+    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    mrun[r] = fminf(mrun[r], m);
+    const float thr = mrun[r] + mma_window(R.qabs[r], bm_run);
+    if (t == (r >> 1)) mythr[r & 1] = thr;
+    const int ql = 16 * (r >> 1) + g + 8 * (r & 1);
+    if (!(tr.c1[r] > thr)) {
+      const int slot = atomicAdd(&wcnt[ql], 1);
+      if (slot < 2) wtile[2 * ql + slot] = (unsigned short)mma_key_tile(tr.c1[r], t);
+    }
+    if (!(tr.c2[r] > thr)) {
+      const int slot = atomicAdd(&wcnt[ql], 1);
+      if (slot < 2) wtile[2 * ql + slot] = (unsigned short)mma_key_tile(tr.c2[r], t);
+    }
+    if (!(tr.c3[r] > thr)) atomicAdd(&wcnt[ql], 3);  // a third tile of this lane: exact scan
+  }
+  __syncwarp();
+
+  int cnt[2], ta[2], tb[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int ql = 16 * t + g + 8 * j;
+    cnt[j] = wcnt[ql];
+    ta[j] = wtile[2 * ql];
+    tb[j] = wtile[2 * ql + 1];
+    // a tile id beyond the staged tiles can only come from padding under a non-finite window
+    if ((cnt[j] >= 1 && ta[j] >= ntile) || (cnt[j] >= 2 && tb[j] >= ntile)) cnt[j] = 3;
+  }
+  refine_tiles<MODE>(s, tgt, c0, nt, ntile, cnt, ta, tb, mythr);
+  __syncwarp();  // lists are reused by the next chunk / job
+}
+
+__device__ __forceinline__ void mma_write(const QueryState<2>& s, int qbase, int lane, float* __restrict__ odist,
+                                          int* __restrict__ oidx, float* __restrict__ mdist, int* __restrict__ midx,
+                                          size_t moff) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    if (!s.valid[j]) continue;
+    const int qi = qbase + 16 * t + g + 8 * j;
+    float d;
+    int i;
+    finish_query<2>(s, j, d, i);
+    odist[qi] = d;
+    oidx[qi] = i;
+    if (mdist != nullptr) {
+      mdist[moff + qi] = d;
+      midx[moff + qi] = i;
+    }
+  }
+}
 
 template <class Cfg, int MODE, int MINB>
 __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const FwdArgs a) {
@@ -44,7 +147,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
   unsigned short* ltile = reinterpret_cast<unsigned short*>(smem + Cfg::kOffTile);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
   const int jpb = a.tiles1 + a.tiles2;
   const int batch = blockIdx.x / jpb;
   const int r0 = blockIdx.x - batch * jpb;
@@ -54,109 +156,139 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
   const int nt = rev ? a.n : a.m;
   const float* qpts = (rev ? a.xyz2 : a.xyz1) + (size_t)batch * nq * 3;
   const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
-  float* odist = (rev ? a.dist2 : a.dist1) + (size_t)batch * nq;
-  int* oidx = (rev ? a.idx2 : a.idx1) + (size_t)batch * nq;
-  float* mdist = rev ? a.mdist2 : a.mdist1;
-  int* midx = rev ? a.midx2 : a.midx1;
 
   const int qbase = qtile * QT + warp * kMmaQW;  // first query of this warp
   MmaRows R;
   mma_load_rows(R, qpts, nq, qbase, lane);
-
-  // The two queries this lane refines and writes: m-tile t, rows g and g+8.
   QueryState<2> s;
-  {
-    const float kInf = __int_as_float(0x7f800000);
-    const float t0x = __ldg(tpts), t0y = __ldg(tpts + 1), t0z = __ldg(tpts + 2);
+  mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane);
+  float mrun[8];
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int qi = qbase + 16 * t + g + 8 * j;
-      s.valid[j] = qi < nq;
-      const int qs = s.valid[j] ? qi : 0;
-      s.qx[j] = __ldg(qpts + (size_t)qs * 3);
-      s.qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
-      s.qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
-      s.qabs[j] = query_abs(s.qx[j], s.qy[j], s.qz[j]);
-      s.ax2[j] = -2.0f * s.qx[j];
-      s.ay2[j] = -2.0f * s.qy[j];
-      s.az2[j] = -2.0f * s.qz[j];
-      s.d0[j] = sqdist<MODE>(t0x, t0y, t0z, s.qx[j], s.qy[j], s.qz[j]);
-      s.best[j] = kInf;
-      s.besti[j] = 0;
-      s.m1g[j] = kInf;
-    }
-  }
-  int* wcnt = lcnt + warp * kMmaQW;
-  unsigned short* wtile = ltile + warp * kMmaQW * 2;
-
-  float mrun[8];  // running minimum of h per row over all chunks (same in the 4 lanes of a quad)
-#pragma unroll
-  for (int r = 0; r < 8; r++) mrun[r] = __int_as_float(0x7f800000);
+  for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
   float bm_run = 0.0f;
 
   for (int c0 = 0; c0 < nt; c0 += CH) {
     const int cn = min(CH, nt - c0);
-    const int ntile = (cn + T - 1) / T;
-    const int nblk = (cn + kMmaBlk - 1) / kMmaBlk;
-    bm_run = fmaxf(bm_run, stage_targets<THREADS, T>(tgt, red, tpts, c0, nt, ntile, tid));
-    stage_bfrag<THREADS>(bfrag, tgt, nblk, cn, tid);
-    wcnt[16 * t + g] = 0;
-    wcnt[16 * t + g + 8] = 0;
+    bm_run = fmaxf(bm_run, stage_targets<THREADS, T>(tgt, red, tpts, c0, nt, (cn + T - 1) / T, tid));
+    stage_bfrag<THREADS>(bfrag, tgt, (cn + kMmaBlk - 1) / kMmaBlk, cn, tid);
     __syncthreads();
-
-    MmaTrack tr;
-    mma_scan(R, reinterpret_cast<const uint2*>(bfrag), nblk, lane, tr);
-
-    // Row minimum over the quad, window, and the qualifying tiles of this lane -> per-query lists.
-    float mythr[2] = {0.0f, 0.0f};
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      float m = tr.c1[r];
-      m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-      m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-      mrun[r] = fminf(mrun[r], m);
-      const float thr = mrun[r] + mma_window(R.qabs[r], bm_run);
-      if (t == (r >> 1)) mythr[r & 1] = thr;
-      const int ql = 16 * (r >> 1) + g + 8 * (r & 1);
-      if (!(tr.c1[r] > thr)) {
-        const int slot = atomicAdd(&wcnt[ql], 1);
-        if (slot < 2) wtile[2 * ql + slot] = (unsigned short)tr.i1[r];
-      }
-      if (!(tr.c2[r] > thr)) {
-        const int slot = atomicAdd(&wcnt[ql], 1);
-        if (slot < 2) wtile[2 * ql + slot] = (unsigned short)tr.i2[r];
-      }
-      if (!(tr.c3[r] > thr)) atomicAdd(&wcnt[ql], 3);  // a third tile of this lane: exact scan
-    }
-    __syncwarp();
-
-    int cnt[2], ta[2], tb[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int ql = 16 * t + g + 8 * j;
-      cnt[j] = wcnt[ql];
-      ta[j] = wtile[2 * ql];
-      tb[j] = wtile[2 * ql + 1];
-      // a tile id beyond the staged tiles can only come from padding (h = +inf) under a
-      // non-finite window: exact scan
-      if ((cnt[j] >= 1 && ta[j] >= ntile) || (cnt[j] >= 2 && tb[j] >= ntile)) cnt[j] = 3;
-    }
-    refine_tiles<T, MODE, 2>(s, tgt, c0, nt, ntile, cnt, ta, tb, mythr);
+    mma_chunk<MODE>(R, s, mrun, tgt, bfrag, c0, nt, cn, bm_run, lcnt + warp * kMmaQW, ltile + warp * kMmaQW * 2, lane);
   }
+  mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
+            rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
+}
 
+// ---- persistent variant: one CTA of 16 warps per SM, warps pull 64-query jobs ----------------
+// The scan is bound by the HMMA pipe (0.5 HMMA.16816 per clock and SM); staging, list building and
+// refine are not.  With one job per warp and a barrier per CTA the phases of the resident warps
+// line up and the tensor pipe idles while they stage or refine; with few CTAs per SM (B=50: 2.7)
+// the last wave is short of work.  Here every SM gets an equal, contiguous share of all
+// (batch, direction, 64-query) jobs.  A share is cut into segments of one target cloud each; the
+// 16 warps stage the cloud once (one 128-target block per warp, no CTA barrier inside), then pull
+// jobs from a shared counter and run scan / refine / write on their own, so that their phases
+// drift apart.  A warp that finds the segment drained stages its block of the NEXT segment into
+// the other buffer before the one barrier per segment.  Clouds of at most 2048 points.
+constexpr int kPersistWarps = 16;
+constexpr int kPersistCH = 2048;
+constexpr size_t kPersistBuf = (size_t)kPersistCH * 16 + (size_t)kPipeU * 32 + (size_t)kPersistCH * 32;
+constexpr size_t kPersistOffRed = 2 * kPersistBuf;                         // [2][16] float
+constexpr size_t kPersistOffCtr = kPersistOffRed + 2 * 16 * 4;             // [2] int (+pad)
+constexpr size_t kPersistOffCnt = kPersistOffCtr + 16;                     // [16][64] int
+constexpr size_t kPersistOffTile = kPersistOffCnt + kPersistWarps * kMmaQW * 4;  // [16][64][2] u16
+constexpr size_t kPersistSmem = kPersistOffTile + kPersistWarps * kMmaQW * 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(kPersistWarps * 32, 1)
+    nn_fwd_mma_persist_kernel(const FwdArgs a, const int wt1, const int wt2, const long long J) {
+  extern __shared__ float4 smem_f4[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
+  float* red = reinterpret_cast<float*>(smem + kPersistOffRed);
+  int* counter = reinterpret_cast<int*>(smem + kPersistOffCtr);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* wcnt = reinterpret_cast<int*>(smem + kPersistOffCnt) + warp * kMmaQW;
+  unsigned short* wtile = reinterpret_cast<unsigned short*>(smem + kPersistOffTile) + warp * kMmaQW * 2;
+
+  const long long jpb = (long long)wt1 + wt2;
+  const long long j0 = J * blockIdx.x / gridDim.x, j1 = J * (blockIdx.x + 1) / gridDim.x;
+
+  // segment of job j: one (batch, direction); this CTA's part of it is [j, pend)
+  auto segment = [&](long long j, int& batch, bool& rev, long long& sbeg, long long& pend) {
+    batch = (int)(j / jpb);
+    const long long r = j - (long long)batch * jpb;
+    rev = r >= wt1;
+    sbeg = (long long)batch * jpb + (rev ? wt1 : 0);
+    const long long send = sbeg + (rev ? wt2 : wt1);
+    pend = send < j1 ? send : j1;
+  };
+  auto stage = [&](int buf, int batch, bool rev) {
+    const int nt = rev ? a.n : a.m;
+    const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
+    float4* tgt = reinterpret_cast<float4*>(smem + buf * kPersistBuf);
+    uint4* bfrag = reinterpret_cast<uint4*>(smem + buf * kPersistBuf + (size_t)kPersistCH * 16 + (size_t)kPipeU * 32);
+    float lmax = 0.0f;
+    if (warp * kMmaBlk < nt) lmax = stage_block_warp(tgt, bfrag, tpts, nt, warp, lane);
+    lmax = warp_max(lmax);
+    if (lane == 0) red[buf * 16 + warp] = lmax;
+  };
+
+  long long j = j0;
+  int k = 0;
+  if (j < j1) {
+    int batch;
+    bool rev;
+    long long sbeg, pend;
+    segment(j, batch, rev, sbeg, pend);
+    stage(0, batch, rev);
+    if (tid == 0) counter[0] = 0;
+  }
+  __syncthreads();
+  while (j < j1) {
+    const int buf = k & 1;
+    int batch;
+    bool rev;
+    long long sbeg, pend;
+    segment(j, batch, rev, sbeg, pend);
+    const int nq = rev ? a.m : a.n;
+    const int nt = rev ? a.n : a.m;
+    const float* qpts = (rev ? a.xyz2 : a.xyz1) + (size_t)batch * nq * 3;
+    const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
+    const float4* tgt = reinterpret_cast<const float4*>(smem + buf * kPersistBuf);
+    const uint4* bfrag =
+        reinterpret_cast<const uint4*>(smem + buf * kPersistBuf + (size_t)kPersistCH * 16 + (size_t)kPipeU * 32);
+    float bm = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
-    if (!s.valid[j]) continue;
-    const int qi = qbase + 16 * t + g + 8 * j;
-    float d;
-    int i;
-    finish_query<2>(s, j, d, i);
-    odist[qi] = d;
-    oidx[qi] = i;
-    if (mdist != nullptr) {
-      mdist[(size_t)batch * nq + qi] = d;
-      midx[(size_t)batch * nq + qi] = i;
+    for (int w = 0; w < 16; w++) bm = fmaxf(bm, red[buf * 16 + w]);
+    if (tid == 0) counter[buf ^ 1] = (int)(pend - j0);  // first job of the next segment
+
+    for (;;) {
+      int jo = 0;
+      if (lane == 0) jo = atomicAdd(&counter[buf], 1);
+      jo = __shfl_sync(0xffffffffu, jo, 0);
+      const long long job = j0 + jo;
+      if (job >= pend) break;
+      const int qbase = (int)(job - sbeg) * kMmaQW;
+      MmaRows R;
+      mma_load_rows(R, qpts, nq, qbase, lane);
+      QueryState<2> s;
+      mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane);
+      float mrun[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
+      mma_chunk<MODE>(R, s, mrun, tgt, bfrag, 0, nt, nt, bm, wcnt, wtile, lane);
+      mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq,
+                (rev ? a.idx2 : a.idx1) + (size_t)batch * nq, rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1,
+                (size_t)batch * nq);
     }
+    if (pend < j1) {  // this warp's block of the next segment, into the other buffer
+      int nb;
+      bool nrev;
+      long long nsbeg, npend;
+      segment(pend, nb, nrev, nsbeg, npend);
+      stage(buf ^ 1, nb, nrev);
+    }
+    __syncthreads();
+    j = pend;
+    k++;
   }
 }
 
@@ -201,7 +333,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) mma_filter_dump_kernel(int n, i
   }
 }
 
-int g_mma_cfg = 0;  // tuning hook (key 7): 0 auto, 1 = 4 warps x 2 CTAs/SM, 2 = 8 warps, 3 = 4 warps x 1024-target chunks
+int g_mma_cfg = 0;  // tuning hook (key 7): 0 auto (= 5); 1-5 = (warps, chunk, CTAs/SM) combinations below
 
 template <class Cfg, int MINB>
 static int launch_fwd_mma_cfg(FwdArgs a, int mode, cudaStream_t st) {
@@ -229,9 +361,37 @@ static int launch_fwd_mma_cfg(FwdArgs a, int mode, cudaStream_t st) {
   return GA_OK;
 }
 
+int g_mma_grid = 0;  // tuning hook (key 8): CTAs of the persistent kernel (0 = one per SM)
+
+int launch_fwd_mma_persist(const FwdArgs& a, int mode, cudaStream_t st) {
+  if (a.n > kPersistCH || a.m > kPersistCH) {
+    set_error("nn_fwd_mma_persist_kernel: clouds of at most %d points", kPersistCH);
+    return GA_ERR_UNSUPPORTED;
+  }
+  const int wt1 = (a.n + kMmaQW - 1) / kMmaQW, wt2 = (a.m + kMmaQW - 1) / kMmaQW;
+  const long long J = (long long)a.b * (wt1 + wt2);
+  if (J <= 0) return GA_OK;
+  auto k = mode == GA_MODE_CPU_EXACT ? nn_fwd_mma_persist_kernel<GA_MODE_CPU_EXACT>
+                                     : nn_fwd_mma_persist_kernel<GA_MODE_GPU_REF>;
+  {
+    static std::atomic<unsigned> done_mask[2];
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done_mask[mode].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPersistSmem));
+      done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
+  }
+  long long grid = g_mma_grid > 0 ? g_mma_grid : sm_count();
+  if (grid > J) grid = J;
+  k<<<(unsigned)grid, kPersistWarps * 32, kPersistSmem, st>>>(a, wt1, wt2, J);
+  GA_LAUNCH_CHECK("nn_fwd_mma_persist_kernel");
+  return GA_OK;
+}
+
 int launch_fwd_mma(const FwdArgs& a, int mode, cudaStream_t st) {
   int cfg = g_mma_cfg;
-  if (cfg == 0) cfg = 1;
+  if (cfg == 0) cfg = 5;  // 8 warps, 128 registers, 2 CTAs per SM: fastest at every measured shape
   switch (cfg) {
     case 2:
       return launch_fwd_mma_cfg<MmaCfg<8, 2048>, 1>(a, mode, st);

@@ -11,11 +11,12 @@
 //   dropped terms   <= 4 * 2^-18 * sum_c |q_c t_c| <= 4 * 2^-18 * 3 A Bm <= 3 * 2^-18 s^2 = 192u s^2
 //   accumulation    16 terms of magnitude <= 3 s^2, hardware adder of >= 24 bits: budget 128u s^2
 //   norm rounding   <= 9u Bm^2
-//   |h - g| <= e2 = 330u s^2.
+//   |h - g| <= e2 = 330u s^2; the scan overwrites 4 low bits of a tile minimum with the tile's
+//   block number (MmaTrack): + 96u s^2.
 // With |d - D| <= e0 = 15u s^2 (reference arithmetic) the reference argmin k* satisfies
-//   h(k*) <= min_j h(j) + 2 e0 + 2 e2 = min h + 690u s^2,
+//   h(k*) <= min_j h(j) + 2 e0 + 2 (e2 + 96u s^2) = min h + 882u s^2,
 // and with |f - g| <= e1 = 18.1u s^2 (the fp32 filter of nn_tiles.cuh)
-//   f(k*) <= min h + 2 e0 + e1 + e2 = min h + 378u s^2.
+//   f(k*) <= min h + 2 e0 + e1 + e2 + 96u s^2 = min h + 474u s^2.
 // One window W2 = 1024u s^2 = 2^-14 s^2 (s inflated by 1.0001, plus an absolute term for
 // flushed denormals) is used for both tests.  tests/test_mma_filter_gpu.py measures |h - g| on
 // the device (ga_debug_mma_filter) and checks it against e2.
@@ -66,39 +67,69 @@ __device__ __forceinline__ int mma_col_target(int blk, int j, int c) {
   return blk * kMmaBlk + 32 * (c >> 1) + 2 * j + (c & 1);
 }
 
-// Build the B fragments of `nblk` blocks from the pair-SoA staging of nn_tiles.cuh
-// (targets >= cn are padding: h = +inf).  Call between two __syncthreads().
+// B fragment (32 bytes) of staged target `tau` of a chunk with `cn` valid targets, from the
+// pair-SoA staging of nn_tiles.cuh; targets >= cn are padding (h = 1e38: far away but finite, so
+// that a key never becomes a NaN bit pattern).
+__device__ __forceinline__ void make_bfrag(uint4* __restrict__ dst, const float4* __restrict__ tgt, int tau, int cn) {
+  const bool ok = tau < cn;
+  const float* pu = reinterpret_cast<const float*>(tgt + 2 * (tau >> 1)) + (tau & 1);
+  const float x = ok ? pu[0] : 0.0f, y = ok ? pu[2] : 0.0f, z = ok ? pu[4] : 0.0f;
+  const float n = ok ? pu[6] : 1.0e38f;
+  const float xr = x - bf16r(x), yr = y - bf16r(y), zr = z - bf16r(z);
+  const float nr = n - bf16r(n);
+  const float nr2 = nr - bf16r(nr);
+  dst[0] = make_uint4(pack_bf16(x, xr), pack_bf16(x, n), pack_bf16(y, yr), pack_bf16(y, nr));
+  dst[1] = make_uint4(pack_bf16(z, zr), pack_bf16(z, nr2), pack_bf16(xr, yr), pack_bf16(zr, 0.0f));
+}
+
+// Build the B fragments of `nblk` blocks (whole CTA).  Call between two __syncthreads().
 template <int THREADS>
 __device__ __forceinline__ void stage_bfrag(uint4* __restrict__ bfrag, const float4* __restrict__ tgt, int nblk,
                                             int cn, int tid) {
-  const float kInf = __int_as_float(0x7f800000);
   const int total = nblk * kMmaBlk;
   for (int p = tid; p < total; p += THREADS) {
     const int c = p & 7, j = (p >> 3) & 15, blk = p >> 7;
-    const int tau = mma_col_target(blk, j, c);
-    const bool ok = tau < cn;
-    const float* pu = reinterpret_cast<const float*>(tgt + 2 * (tau >> 1)) + (tau & 1);
-    const float x = ok ? pu[0] : 0.0f, y = ok ? pu[2] : 0.0f, z = ok ? pu[4] : 0.0f;
-    const float n = ok ? pu[6] : kInf;
-    const float xr = x - bf16r(x), yr = y - bf16r(y), zr = z - bf16r(z);
-    float nr = n - bf16r(n);
-    float nr2 = nr - bf16r(nr);
-    if (!ok) nr = nr2 = 0.0f;  // keep the padding a clean +inf
-    bfrag[2 * p] = make_uint4(pack_bf16(x, xr), pack_bf16(x, n), pack_bf16(y, yr), pack_bf16(y, nr));
-    bfrag[2 * p + 1] = make_uint4(pack_bf16(z, zr), pack_bf16(z, nr2), pack_bf16(xr, yr), pack_bf16(zr, 0.0f));
+    make_bfrag(bfrag + 2 * p, tgt, mma_col_target(blk, j, c), cn);
   }
 }
 
-// A-fragment registers of one query row for quad lane t.
-__device__ __forceinline__ void mma_afrag_row(float qx, float qy, float qz, int t, uint32_t& lo, uint32_t& hi) {
-  const float X = -2.0f * qx, Y = -2.0f * qy, Z = -2.0f * qz;
-  const float Xr = X - bf16r(X), Yr = Y - bf16r(Y), Zr = Z - bf16r(Z);
-  const float C = t == 0 ? X : (t == 1 ? Y : Z);
-  const float Cr = t == 0 ? Xr : (t == 1 ? Yr : Zr);
-  const uint32_t lo_c = pack_bf16(C, C), hi_c = pack_bf16(Cr, 1.0f);
-  const uint32_t lo_3 = pack_bf16(Xr, Yr), hi_3 = pack_bf16(Zr, 0.0f);
-  lo = t < 3 ? lo_c : lo_3;
-  hi = t < 3 ? hi_c : hi_3;
+// One WARP stages MMA block `blk` of a cloud (targets [128 blk, +128) of `tpts`, nt points):
+// pair-SoA first, then the B fragments built from it.  No CTA barrier: the block is self-contained.
+// Returns this lane's partial max |coordinate| (NaNs dropped).
+__device__ __forceinline__ float stage_block_warp(float4* __restrict__ tgt, uint4* __restrict__ bfrag,
+                                                  const float* __restrict__ tpts, int nt, int blk, int lane) {
+  const float kInf = __int_as_float(0x7f800000);
+  float lmax = 0.0f;
+  float c[2][6];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int g = 2 * (64 * blk + 32 * s + lane);
+#pragma unroll
+    for (int e = 0; e < 6; e++) c[s][e] = g + (e >= 3) < nt ? __ldg(tpts + (size_t)g * 3 + e) : 0.0f;
+  }
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int p = 64 * blk + 32 * s + lane;
+    const int g = 2 * p;
+    float n0 = kInf, n1 = kInf;
+    if (g < nt) {
+      n0 = fmaf(c[s][2], c[s][2], fmaf(c[s][1], c[s][1], c[s][0] * c[s][0]));
+      lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(c[s][0]), fabsf(c[s][1])), fabsf(c[s][2])));
+    }
+    if (g + 1 < nt) {
+      n1 = fmaf(c[s][5], c[s][5], fmaf(c[s][4], c[s][4], c[s][3] * c[s][3]));
+      lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(c[s][3]), fabsf(c[s][4])), fabsf(c[s][5])));
+    }
+    tgt[2 * p] = make_float4(c[s][0], c[s][3], c[s][1], c[s][4]);
+    tgt[2 * p + 1] = make_float4(c[s][2], c[s][5], n0, n1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int q = lane + 32 * i;  // item of this block: column c = q & 7 of n-tile j = q >> 3
+    make_bfrag(bfrag + 2 * (blk * kMmaBlk + q), tgt, mma_col_target(blk, q >> 3, q & 7), nt);
+  }
+  return lmax;
 }
 
 // Per-lane view of the warp's 64 queries: 8 rows (m-tile i = r>>1, half h = r&1: local query
@@ -108,44 +139,60 @@ struct MmaRows {
   float qabs[8];
 };
 
+// Quad lane t < 3 loads and splits coordinate t of each of its rows (A slots C1, C1, C2, 1); lane 3
+// needs the three residuals (X2, Y2, Z2, 0), which it gets from lanes 0..2 by shuffle.  The max
+// |coordinate| of a row is a quad reduction (+inf when a coordinate is NaN, as query_abs).
 __device__ __forceinline__ void mma_load_rows(MmaRows& R, const float* __restrict__ qpts, int nq, int qbase,
                                               int lane) {
   const int g = lane >> 2, t = lane & 3;
+  const int cc = t < 3 ? t : 2;
+  const unsigned qbaseLane = lane & ~3;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const int i = r >> 1, h = r & 1;
     const int qi = qbase + 16 * i + g + 8 * h;
     const int qs = qi < nq ? qi : 0;
-    const float x = __ldg(qpts + (size_t)qs * 3), y = __ldg(qpts + (size_t)qs * 3 + 1),
-                z = __ldg(qpts + (size_t)qs * 3 + 2);
-    R.qabs[r] = query_abs(x, y, z);
-    mma_afrag_row(x, y, z, t, R.a[i][h], R.a[i][2 + h]);
+    const float q = __ldg(qpts + (size_t)qs * 3 + cc);
+    const float C = -2.0f * q;
+    const float Cr = C - bf16r(C);
+    const float Xr = __shfl_sync(0xffffffffu, Cr, qbaseLane), Yr = __shfl_sync(0xffffffffu, Cr, qbaseLane + 1),
+                Zr = __shfl_sync(0xffffffffu, Cr, qbaseLane + 2);
+    const uint32_t lo_c = pack_bf16(C, C), hi_c = pack_bf16(Cr, 1.0f);
+    const uint32_t lo_3 = pack_bf16(Xr, Yr), hi_3 = pack_bf16(Zr, 0.0f);
+    R.a[i][h] = t < 3 ? lo_c : lo_3;
+    R.a[i][2 + h] = t < 3 ? hi_c : hi_3;
+    float a = q != q ? __int_as_float(0x7f800000) : fabsf(q);
+    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 2));
+    R.qabs[r] = a;
   }
 }
 
-// The three smallest tile minima per row and the tiles of the two smallest (this lane's tiles only).
+// Sentinel for "no value": finite, so that a key never turns into a NaN bit pattern.
+constexpr float kMmaBig = 3.0e38f;
+
+// The three smallest tile keys per row (this lane's tiles only).  A key is the tile minimum of h
+// with its low 4 mantissa bits replaced by the block number (the tile is 4 blk + t): the three
+// smallest tiles AND their identities come out of five FMNMX per tile and row.  Overwriting 4
+// bits moves a value by < 16 ulp <= 96u s^2, which the window W2 absorbs (nn_mma.cuh header:
+// 2 e0 + 2 (e2 + 96u) = 882u < 1024u).
 struct MmaTrack {
   float c1[8], c2[8], c3[8];
-  int i1[8], i2[8];
 };
+__device__ __forceinline__ int mma_key_tile(float key, int t) { return ((__float_as_int(key) & 15) << 2) + t; }
 
-// Tensor-core filter scan over `nblk` staged blocks.  Lane (g,t) sees, for each of its 8 rows,
-// the minimum of h over the 32 contiguous targets [128 blk + 32 t, +32) of every block, i.e.
+// Tensor-core filter scan over `nblk` (<= 16) staged blocks.  Lane (g,t) sees, for each of its 8
+// rows, the minimum of h over the 32 contiguous targets [128 blk + 32 t, +32) of every block, i.e.
 // over refine tile 4 blk + t, without any cross-lane traffic.
 __device__ __forceinline__ void mma_scan(const MmaRows& R, const uint2* __restrict__ bfrag, int nblk, int lane,
                                          MmaTrack& tr) {
-  const float kInf = __int_as_float(0x7f800000);
-  const int t = lane & 3;
 #pragma unroll
-  for (int r = 0; r < 8; r++) {
-    tr.c1[r] = tr.c2[r] = tr.c3[r] = kInf;
-    tr.i1[r] = tr.i2[r] = 0;
-  }
+  for (int r = 0; r < 8; r++) tr.c1[r] = tr.c2[r] = tr.c3[r] = kMmaBig;
 #pragma unroll 1
   for (int blk = 0; blk < nblk; blk++) {
     float rm[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) rm[r] = kInf;
+    for (int r = 0; r < 8; r++) rm[r] = kMmaBig;
     const uint2* bp = bfrag + (size_t)blk * 16 * 32 + lane;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
@@ -158,47 +205,107 @@ __device__ __forceinline__ void mma_scan(const MmaRows& R, const uint2* __restri
         rm[2 * i + 1] = fmin3(rm[2 * i + 1], c[2], c[3]);
       }
     }
-    const int tile = blk * 4 + t;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      const float tm = rm[r];
-      const bool lt1 = tm < tr.c1[r], lt2 = tm < tr.c2[r];
-      tr.c3[r] = fminf(tr.c3[r], fmaxf(tr.c2[r], tm));
-      tr.i2[r] = lt1 ? tr.i1[r] : (lt2 ? tile : tr.i2[r]);
-      tr.c2[r] = fminf(tr.c2[r], fmaxf(tr.c1[r], tm));
-      tr.i1[r] = lt1 ? tile : tr.i1[r];
-      tr.c1[r] = fminf(tr.c1[r], tm);
+      const float key = __int_as_float((__float_as_int(rm[r]) & ~15) | blk);
+      tr.c3[r] = fminf(tr.c3[r], fmaxf(tr.c2[r], key));
+      tr.c2[r] = fminf(tr.c2[r], fmaxf(tr.c1[r], key));
+      tr.c1[r] = fminf(tr.c1[r], key);
     }
   }
 }
 
-// Refine: exact evaluation of up to two tiles per query (tile ids ta, tb; cnt of them valid),
-// candidates selected by the fp32 filter against thr; cnt > 2 or more than two candidates send the
-// query to the cooperative exact scan.  Same structure as search_phase2.
-template <int T, int MODE, int Q>
-__device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __restrict__ tgt, int c0, int nt,
-                                             int ntile, const int (&cnt)[Q], const int (&ta)[Q], const int (&tb)[Q],
-                                             const float (&thr)[Q]) {
-  const int lane = threadIdx.x & 31;
+// Candidate bit mask of one 32-target tile for one query: bit k set <=> the fp32 filter of target
+// g0 + k is <= thr (NaN counts as a candidate).  Lanes of a warp usually walk DIFFERENT tiles,
+// which are a multiple of 512 B apart: each lane starts at its own pair (conflict-free), collects
+// the bits in walk order with immediate masks, and rotates the word back once at the end.
+__device__ __forceinline__ unsigned tile_candidate_mask(const float4* __restrict__ tp, float ax2, float ay2,
+                                                        float az2, float thr) {
+  constexpr int T = kMmaT;
+  const int rot = threadIdx.x & (T / 2 - 1);
+  unsigned m = 0;
 #pragma unroll
-  for (int j = 0; j < Q; j++) {
-    bool hard = false;
-    if (s.valid[j]) {
-      hard = cnt[j] > 2;
-      if (!hard) {
-        int n = 0, ca = 0, cb = 0;
-        if (cnt[j] >= 1)
-          scan_tile_candidates<T>(tgt + (size_t)ta[j] * T, c0 + ta[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr[j], n,
-                                  ca, cb);
-        if (cnt[j] >= 2)
-          scan_tile_candidates<T>(tgt + (size_t)tb[j] * T, c0 + tb[j] * T, nt, s.ax2[j], s.ay2[j], s.az2[j], thr[j], n,
-                                  ca, cb);
-        if (n >= 1 && n <= 2) eval_candidate<MODE>(tgt, c0, ca, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
-        if (n == 2) eval_candidate<MODE>(tgt, c0, cb, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
-        hard = n > 2;
+  for (int i = 0; i < T / 2; i++) {
+    const int pp = (i + rot) & (T / 2 - 1);
+    const float2 f = filter_pair(tp[2 * pp], tp[2 * pp + 1], ax2, ay2, az2);
+    m |= (!(f.x > thr) ? (1u << (2 * i)) : 0u) | (!(f.y > thr) ? (2u << (2 * i)) : 0u);
+  }
+  return __funnelshift_l(m, m, 2 * rot);  // walk position i holds pair (i + rot) mod 16
+}
+
+// Refine for the tensor-core scan.  Per query: cnt qualifying tiles (ta, tb valid for cnt <= 2).
+//  1. first tile, one lane per query: fp32 filter -> candidate mask -> one or two exact evaluations
+//     (all lanes in step); more than two candidates -> exact warp scan of the chunk;
+//  2. second tiles are rare (a few per warp): the whole warp evaluates such a tile exactly, one
+//     target per lane, and merges by (value, index);
+//  3. cnt > 2 / many candidates / non-finite window: warp_exact_scan (nn_search.cuh).
+template <int MODE>
+__device__ __forceinline__ void refine_tiles(QueryState<2>& s, const float4* __restrict__ tgt, int c0, int nt,
+                                             int ntile, const int (&cnt)[2], const int (&ta)[2], const int (&tb)[2],
+                                             const float (&thr)[2]) {
+  constexpr int T = kMmaT;
+  const int lane = threadIdx.x & 31;
+  bool hard[2], second[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    hard[j] = s.valid[j] && cnt[j] > 2;
+    second[j] = s.valid[j] && cnt[j] == 2;
+    unsigned mask = 0;
+    int g0 = 0;
+    if (s.valid[j] && cnt[j] >= 1 && cnt[j] <= 2) {
+      g0 = c0 + ta[j] * T;
+      const int rem = nt - g0;  // >= 1: only staged tiles are listed
+      mask = tile_candidate_mask(tgt + (size_t)ta[j] * T, s.ax2[j], s.ay2[j], s.az2[j], thr[j]);
+      mask &= rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    }
+    const int n = __popc(mask);
+    if (n >= 1 && n <= 2)
+      eval_candidate<MODE>(tgt, c0, g0 + __ffs(mask) - 1, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+    if (n == 2)
+      eval_candidate<MODE>(tgt, c0, g0 + 31 - __clz(mask), s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+    if (n > 2) {
+      hard[j] = true;
+      second[j] = false;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    unsigned pending = __ballot_sync(0xffffffffu, second[j]);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const float bqx = __shfl_sync(0xffffffffu, s.qx[j], src), bqy = __shfl_sync(0xffffffffu, s.qy[j], src),
+                  bqz = __shfl_sync(0xffffffffu, s.qz[j], src);
+      const int tile = __shfl_sync(0xffffffffu, tb[j], src);
+      const int gl = tile * T + lane;  // chunk-local target of this lane
+      const float* pu = reinterpret_cast<const float*>(tgt + 2 * (gl >> 1)) + (gl & 1);
+      float b = __int_as_float(0x7f800000);
+      int bi = 0x7fffffff;
+      if (c0 + gl < nt) {
+        const float d = sqdist<MODE>(pu[0], pu[2], pu[4], bqx, bqy, bqz);
+        if (d < b) {  // NaN is never selected
+          b = d;
+          bi = c0 + gl;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+        const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < b || (ob == b && obi < bi)) {
+          b = ob;
+          bi = obi;
+        }
+      }
+      if (lane == src && (b < s.best[j] || (b == s.best[j] && bi < s.besti[j]))) {
+        s.best[j] = b;
+        s.besti[j] = bi;
       }
     }
-    unsigned pending = __ballot_sync(0xffffffffu, hard);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    unsigned pending = __ballot_sync(0xffffffffu, hard[j]);
     while (pending) {
       const int src = __ffs(pending) - 1;
       pending &= pending - 1;

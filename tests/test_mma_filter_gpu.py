@@ -11,7 +11,7 @@ from util import bits_equal, cloud
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 U = 2.0 ** -24
-MMA_CFGS = [1, 2, 3, 4, 5]
+MMA_CFGS = [1, 2, 3, 4, 5, 21, 1021, 7021]  # 21: persistent kernel (one CTA per SM); G*1000+21: G CTAs
 
 
 def t(a):
@@ -48,13 +48,18 @@ def test_filter_values_within_documented_bound(ga, n, m, scale):
 
 
 def run_variant(ga, lib, a, b, cfg, mode=0):
-    lib.ga_set_tuning(0, 20)
-    lib.ga_set_tuning(7, cfg)
+    if cfg % 1000 == 21:
+        lib.ga_set_tuning(0, 21)
+        lib.ga_set_tuning(8, cfg // 1000)
+    else:
+        lib.ga_set_tuning(0, 20)
+        lib.ga_set_tuning(7, cfg)
     try:
         return [x.cpu().numpy() for x in ga.nn_distance(t(a), t(b), mode)]
     finally:
         lib.ga_set_tuning(0, 0)
         lib.ga_set_tuning(7, 0)
+        lib.ga_set_tuning(8, 0)
 
 
 def check(ga, oracle, a, b, mode=0, cfgs=MMA_CFGS):
@@ -62,6 +67,8 @@ def check(ga, oracle, a, b, mode=0, cfgs=MMA_CFGS):
     lib = _lib.load()
     want = oracle.nn_distance(a, b, mode)
     for cfg in cfgs:
+        if cfg % 1000 == 21 and (a.shape[1] > 2048 or b.shape[1] > 2048 or a.shape[1] == 0 or b.shape[1] == 0):
+            continue  # the persistent kernel takes clouds of at most 2048 points
         got = run_variant(ga, lib, a, b, cfg, mode)
         for nme, g, w in zip(["dist1", "idx1", "dist2", "idx2"], got, want):
             assert bits_equal(g, w), "%s differs (shape %s vs %s, mode %d, mma cfg %d): %d mismatches" % (
@@ -82,7 +89,8 @@ def test_ragged_shapes(ga, oracle, shape):
 
 
 def test_batch_of_8(ga, oracle):
-    check(ga, oracle, cloud(21, (8, 2048, 3)), cloud(22, (8, 2048, 3)), cfgs=[1, 4])
+    check(ga, oracle, cloud(21, (8, 2048, 3)), cloud(22, (8, 2048, 3)), cfgs=[1, 4, 21, 3021, 29021])
+    check(ga, oracle, cloud(23, (9, 1000, 3)), cloud(24, (9, 777, 3)), cfgs=[21, 2021, 5021, 13021])
 
 
 def test_adversarial_duplicates_and_grids(ga, oracle):
@@ -101,7 +109,7 @@ def test_scales_and_offsets(ga, oracle):
     a, b = cloud(31, (1, 1500, 3)), cloud(32, (1, 1800, 3))
     for scale, off in [(1e3, 0.0), (1.0, 100.0), (1e-6, 0.0), (1e-18, 0.0), (1e15, 0.0), (1e-30, 0.0)]:
         check(ga, oracle, (a * np.float32(scale) + np.float32(off)).astype(np.float32),
-              (b * np.float32(scale) + np.float32(off)).astype(np.float32), cfgs=[1, 4])
+              (b * np.float32(scale) + np.float32(off)).astype(np.float32), cfgs=[1, 4, 21])
 
 
 def test_non_finite_inputs(ga, oracle):
@@ -111,8 +119,8 @@ def test_non_finite_inputs(ga, oracle):
     b[1, 17, 2] = np.inf
     a[1, 3, 0] = -np.inf
     b[1, 100] = 3e38             # overflowing distances
-    check(ga, oracle, a, b, cfgs=[1, 4])
-    check(ga, oracle, a, b, mode=1, cfgs=[1])
+    check(ga, oracle, a, b, cfgs=[1, 4, 21])
+    check(ga, oracle, a, b, mode=1, cfgs=[1, 21])
 
 
 def test_full_size_equals_plain_kernel(ga):

@@ -35,7 +35,7 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // MODE 2: as 1 without the FMNMX3 (results folded with one add per MMA to keep them alive)
 // MODE 3: as 1 with B kept in registers (no LDS)
 template <int MODE, int MT>
-__global__ void __launch_bounds__(256) bench(float* out, int steps, long long* cyc) {
+__global__ void __launch_bounds__(512) bench(float* out, int steps, long long* cyc) {
   __shared__ uint2 bfrag[64 * 32];
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) bfrag[i] = make_uint2(0x3f803f80u + i, 0x3f803f80u);
@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(256) bench(float* out, int steps, long long* c
 #pragma unroll
     for (int r = 0; r < 4; r++) c[i][r] = 0.f;
   }
+  long long g0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g0));
   const long long t0 = clock64();
   uint2 bf = bfrag[lane];
 #pragma unroll 4
@@ -76,11 +78,16 @@ __global__ void __launch_bounds__(256) bench(float* out, int steps, long long* c
     if (MODE == 3) bf.x += 1;
   }
   const long long t1 = clock64();
+  long long g1;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
   float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < MT; i++) acc += rm[i][0] + rm[i][1] + c[i][0] + c[i][1] + c[i][2] + c[i][3];
   if (acc == 123.456f) out[0] = acc;
-  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    cyc[0] = t1 - t0;
+    cyc[1] = g1 - g0;
+  }
 }
 
 template <int MODE, int MT>
@@ -88,10 +95,10 @@ static void run(const char* name, int warps_per_sm, int sms) {
   float* out;
   long long* cyc;
   CK(cudaMalloc(&out, 4));
-  CK(cudaMalloc(&cyc, 8));
+  CK(cudaMalloc(&cyc, 16));
   const int steps = 1 << 14;
-  const int threads = warps_per_sm >= 8 ? 256 : warps_per_sm * 32;
-  const int ctas_per_sm = warps_per_sm * 32 / threads;
+  const int threads = warps_per_sm * 32;  // one CTA per SM: residency is not in question
+  const int ctas_per_sm = 1;
   bench<MODE, MT><<<sms * ctas_per_sm, threads>>>(out, steps, cyc);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
@@ -103,14 +110,15 @@ static void run(const char* name, int warps_per_sm, int sms) {
   CK(cudaEventSynchronize(e1));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
-  long long h = 0;
-  CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+  long long hh[2] = {0, 0};
+  CK(cudaMemcpy(hh, cyc, 16, cudaMemcpyDeviceToHost));
+  const long long h = hh[0];
   const double clk_per_step_warp = (double)h / steps;                    // one warp's view
   const double clk_per_step_sm = clk_per_step_warp / warps_per_sm;       // SM cycles per warp-step
   const double evals_per_clk_sm = (double)MT * 128.0 / clk_per_step_sm;  // 16x8 outputs per MMA
   const double mma_per_clk_sm = (double)MT / clk_per_step_sm;
-  printf("%-28s MT=%d warps/SM=%2d  %.2f ms  clk/step/warp=%7.2f  MMA/clk/SM=%.3f  evals/clk/SM=%.1f\n", name, MT,
-         warps_per_sm, ms, clk_per_step_warp, mma_per_clk_sm, evals_per_clk_sm);
+  printf("%-28s MT=%d warps/SM=%2d  %.2f ms  clk/step/warp=%7.2f  MMA/clk/SM=%.3f  evals/clk/SM=%.1f  SM clock %.2f GHz\n",
+         name, MT, warps_per_sm, ms, clk_per_step_warp, mma_per_clk_sm, evals_per_clk_sm, (double)h / (double)hh[1]);
   cudaFree(out);
   cudaFree(cyc);
 }
@@ -121,10 +129,9 @@ int main() {
   printf("device %s, %d SMs\n", p.name, p.multiProcessorCount);
   const int sms = p.multiProcessorCount;
   for (int w : {4, 8, 16}) run<0, 4>("hmma chained", w, sms);
-  for (int w : {4, 8, 16}) run<0, 8>("hmma chained", w, sms);
   for (int w : {4, 8, 16}) run<2, 4>("hmma zeroC + lds", w, sms);
   for (int w : {4, 8, 16}) run<3, 4>("hmma zeroC + 2 fmnmx3 (regs)", w, sms);
-  for (int w : {4, 8, 16}) run<1, 4>("hmma zeroC + lds + 2 fmnmx3", w, sms);
-  for (int w : {4, 8, 16}) run<1, 2>("hmma zeroC + lds + 2 fmnmx3", w, sms);
+  for (int w : {4, 8, 12, 16}) run<1, 4>("hmma zeroC + lds + 2 fmnmx3", w, sms);
+  for (int w : {4, 8, 12, 16}) run<1, 2>("hmma zeroC + lds + 2 fmnmx3", w, sms);
   return 0;
 }

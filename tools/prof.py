@@ -13,6 +13,9 @@ what = sys.argv[1] if len(sys.argv) > 1 else "all"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 N = 2048
 lib = _lib.load()
+for kv in os.environ.get("GA_TUNE", "").split(","):  # e.g. GA_TUNE=0=20,7=5
+    if "=" in kv:
+        lib.ga_set_tuning(int(kv.split("=")[0]), int(kv.split("=")[1]))
 dev = torch.device("cuda:0")
 p = ctypes.c_void_p
 st = torch.cuda.current_stream().cuda_stream
