@@ -18,6 +18,7 @@ extern int g_fwd_split;       // nn_distance_fwd.cu
 extern int g_fwd_split_q;     // nn_distance_fwd.cu
 extern int g_mma_cfg;         // nn_distance_fwd_mma.cu
 extern int g_mma_grid;        // nn_distance_fwd_mma.cu
+extern int g_bwd_split;       // nn_distance_bwd.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -118,6 +119,10 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 8) {
     ga::g_mma_grid = value;
+    return GA_OK;
+  }
+  if (key == 9) {
+    ga::g_bwd_split = value;
     return GA_OK;
   }
   ga::set_error("ga_set_tuning: unknown key %d", key);

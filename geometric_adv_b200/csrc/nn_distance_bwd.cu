@@ -23,10 +23,13 @@ namespace ga {
 
 constexpr int kBwdThreads = 512;
 constexpr int kBwdWarps = kBwdThreads / 32;
-constexpr int kBwdKeys = 2048;  // keys (output points) handled per pass
+// keys (output points) handled per pass: 2048 = one CTA per (batch element, cloud); 512 = the
+// output points of a cloud are split over up to 4 CTAs, each of which walks all contributors
+// but counts only the keys of its own range (4x the CTAs for the 148 SMs at attack batch sizes)
 
 struct BwdArgs {
   int b, n, m;
+  int nparts;  // CTAs per (batch element, cloud)
   const float* xyz1;
   const float* xyz2;
   const float* gd1;
@@ -38,12 +41,14 @@ struct BwdArgs {
 };
 
 // smem: cnt[W][K] u16 | total[K] i32 | start[K] i32 | wsum[W] i32 | order[L] u16
-static size_t bwd_smem_bytes(int lmax) {
-  return (size_t)kBwdWarps * kBwdKeys * 2 + (size_t)kBwdKeys * 4 * 2 + 64 * 4 + (((size_t)lmax * 2 + 15) & ~(size_t)15);
+static size_t bwd_smem_bytes(int keys, int lmax) {
+  return (size_t)kBwdWarps * keys * 2 + (size_t)keys * 4 * 2 + 64 * 4 + (((size_t)lmax * 2 + 15) & ~(size_t)15);
 }
 
+template <int K>
 __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
-  constexpr int W = kBwdWarps, K = kBwdKeys;
+  constexpr int W = kBwdWarps;
+  static_assert(K % kBwdThreads == 0, "whole keys per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned short* cnt = reinterpret_cast<unsigned short*>(smem_raw);            // [W][K]
   int* total = reinterpret_cast<int*>(smem_raw + (size_t)W * K * 2);           // [K]
@@ -52,8 +57,9 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
   unsigned short* order = reinterpret_cast<unsigned short*>(wsum + 64);        // [L]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int batch = blockIdx.x >> 1;
-  const int side = blockIdx.x & 1;
+  const int part = blockIdx.x % a.nparts;
+  const int batch = (blockIdx.x / a.nparts) >> 1;
+  const int side = (blockIdx.x / a.nparts) & 1;
   // own = the cloud whose gradient this CTA produces (P points); oth = the other (L points)
   const int P = side ? a.m : a.n;
   const int L = side ? a.n : a.m;
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
   const int e_end = min(L, e_begin + seg);
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int k0 = 0; k0 < P; k0 += K) {
+  for (int k0 = part * K; k0 < P; k0 += a.nparts * K) {
     const int kn = min(K, P - k0);
     // 1. zero the per-warp count tables
     {
@@ -245,6 +251,8 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
   }
 }
 
+int g_bwd_split = -1;  // tuning hook (key 9): -1 auto, 0 one CTA per cloud, 1 output points split over 4 CTAs
+
 }  // namespace ga
 
 extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const float* xyz2,
@@ -269,28 +277,40 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
     set_error("ga_nn_distance_bwd: clouds larger than 65536 points are not supported (n=%d m=%d)", n, m);
     return GA_ERR_UNSUPPORTED;
   }
-  if ((long long)b * 2 > 0x7fffffffLL) {
+  if ((long long)b * 8 > 0x7fffffffLL) {
     set_error("ga_nn_distance_bwd: batch too large");
     return GA_ERR_UNSUPPORTED;
-  }
-  const size_t smem = bwd_smem_bytes(lmax);
-  {
-    // raise the opt-in shared-memory limit once per device to the largest size the kernel can ask for
-    static std::atomic<unsigned> done_mask{0};
-    int dev = 0;
-    GA_CUDA_TRY(cudaGetDevice(&dev));
-    if (!(done_mask.load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
-      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)bwd_smem_bytes(65536)));
-      done_mask.fetch_or(1u << (dev & 31), std::memory_order_relaxed);
-    }
   }
   BwdArgs a;
   a.b = b; a.n = n; a.m = m;
   a.xyz1 = xyz1; a.xyz2 = xyz2;
   a.gd1 = grad_dist1; a.idx1 = idx1; a.gd2 = grad_dist2; a.idx2 = idx2;
   a.gxyz1 = grad_xyz1; a.gxyz2 = grad_xyz2;
-  nn_bwd_kernel<<<(unsigned)(2 * b), kBwdThreads, smem, st>>>(a);
+  // Up to one wave of split CTAs: split the output points (measured, 2048-point clouds: B=1 17.4 ->
+  // 14.3 us, B=10 18.4 -> 14.3 us); more cloud pairs: one CTA per cloud walks the contributors only
+  // once (B=50 18.4 vs 27.5 us split, B=512 82 vs 184 us).
+  int split = g_bwd_split;
+  if (split < 0) split = (long long)b * 8 <= (long long)sm_count() ? 1 : 0;
+  {
+    // raise the opt-in shared-memory limit once per device to the largest size the kernels can ask for
+    static std::atomic<unsigned> done_mask{0};
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done_mask.load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bwd_smem_bytes(2048, 65536)));
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bwd_smem_bytes(512, 65536)));
+      done_mask.fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
+  }
+  if (split) {
+    a.nparts = (lmax + 511) / 512 < 4 ? (lmax + 511) / 512 : 4;
+    nn_bwd_kernel<512><<<(unsigned)(2 * b * a.nparts), kBwdThreads, bwd_smem_bytes(512, lmax), st>>>(a);
+  } else {
+    a.nparts = 1;
+    nn_bwd_kernel<2048><<<(unsigned)(2 * b), kBwdThreads, bwd_smem_bytes(2048, lmax), st>>>(a);
+  }
   GA_LAUNCH_CHECK("nn_bwd_kernel");
   return GA_OK;
 }

@@ -256,10 +256,20 @@ def test_fwd_bwd_host_entry_point(ga, pinned, path):
 
 # ------------------------------------------------------------------ backward
 def check_bwd(ga, oracle, a, b, gd1, i1, gd2, i2):
-    g1, g2 = ga.nn_distance_grad(t(a), t(b), t(gd1), t(i1), t(gd2), t(i2))
+    """Both launch shapes of the gradient kernel: one CTA per cloud, and output points split over 4 CTAs."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
     w1, w2 = oracle.nn_distance_grad(a, b, gd1, i1, gd2, i2)
-    assert bits_equal(g1.cpu().numpy(), w1), "grad_xyz1: %d mismatches" % int(np.sum(g1.cpu().numpy() != w1))
-    assert bits_equal(g2.cpu().numpy(), w2), "grad_xyz2: %d mismatches" % int(np.sum(g2.cpu().numpy() != w2))
+    for split in (0, 1, -1):
+        lib.ga_set_tuning(9, split)
+        try:
+            g1, g2 = ga.nn_distance_grad(t(a), t(b), t(gd1), t(i1), t(gd2), t(i2))
+        finally:
+            lib.ga_set_tuning(9, -1)
+        assert bits_equal(g1.cpu().numpy(), w1), "grad_xyz1 (split %d): %d mismatches" % (
+            split, int(np.sum(g1.cpu().numpy() != w1)))
+        assert bits_equal(g2.cpu().numpy(), w2), "grad_xyz2 (split %d): %d mismatches" % (
+            split, int(np.sum(g2.cpu().numpy() != w2)))
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 5, 9), (3, 100, 200), (2, 2048, 2048), (1, 2500, 2048),
