@@ -21,6 +21,7 @@ extern int g_mma_grid;        // nn_distance_fwd_mma.cu
 extern int g_bwd_split;       // nn_distance_bwd.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static thread_local const char* t_last_kernel = "";
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -33,6 +34,8 @@ int cuda_fail(cudaError_t e, const char* where) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), where);
   return (int)e;
 }
+
+void note_kernel(const char* name) { t_last_kernel = name; }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -129,6 +132,7 @@ int ga_set_tuning(int key, int value) {
   return GA_ERR_INVALID_ARGUMENT;
 }
 const char* ga_last_error(void) { return t_err; }
+const char* ga_last_kernel(void) { return t_last_kernel; }
 long long ga_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // tf_nndistance.cpp:51-58

@@ -15,6 +15,7 @@ namespace ga {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* where);
 void count_launch(int n = 1);
+void note_kernel(const char* name);
 int sm_count();
 
 #define GA_CUDA_TRY(expr)                                   \
@@ -28,6 +29,7 @@ int sm_count();
     cudaError_t _e = cudaGetLastError();                      \
     if (_e != cudaSuccess) return ga::cuda_fail(_e, what);    \
     ga::count_launch();                                       \
+    ga::note_kernel(what);                                    \
   } while (0)
 
 static inline cudaStream_t as_stream(ga_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

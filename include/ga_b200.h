@@ -170,6 +170,9 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
 int ga_set_tuning(int key, int value);
 /* Empty-kernel launch floor in microseconds (average over `reps` launches). */
 int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);
+/* Name of the kernel the calling thread launched last through this library ("" before the
+ * first launch).  bench.py names the roofline kernel with it instead of assuming the dispatch. */
+const char* ga_last_kernel(void);
 /* Evidence for the tensor-core filter (forward variant 20, nn_mma.cuh): the raw filter values
  * h(q,t) ~ |t|^2 - 2 q.t of one cloud pair, out[q*m + t], n queries (xyz1), m <= 2048 targets
  * (xyz2), device pointers.  Tests compare it with the fp64 value against the documented bound. */

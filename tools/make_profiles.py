@@ -15,12 +15,16 @@ for rep in sorted(os.listdir(G)):
         if len(rows) >= 3:
             h, v = rows[0], rows[2]
             d = dict(zip(h, v))
-            if "nn_fwd" in d.get("Kernel Name", ""):
+            kn = d.get("Kernel Name", "").split("(")[0].split("<")[0].split("::")[-1]
+            if kn.startswith("nn_fwd") and "_fwd" in rep:
                 def mb(x):
                     return float(d[x]) * 1e6 if d.get(x) else 0.0
-                tr = {"nn_fwd_kernel_b50_dram_bytes_per_launch": mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum"),
-                      "source": rep, "note": "dram__bytes_read.sum + dram__bytes_write.sum (Mbyte units in the report)"}
-                json.dump(tr, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+                tp = os.path.join(P, "traffic.json")
+                tr = json.load(open(tp)) if os.path.exists(tp) else {}
+                tr[kn + "_b50_dram_bytes_per_launch"] = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
+                tr[kn + "_source"] = rep
+                tr["note"] = "dram__bytes_read.sum + dram__bytes_write.sum (Mbyte units in the report)"
+                json.dump(tr, open(tp, "w"), indent=1)
 for name in ("tune.json", "microbench.txt", "loopbench.txt", "bench_%s.json" % tag):
     src = os.path.join(G, name)
     if os.path.exists(src):
