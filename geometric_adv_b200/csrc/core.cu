@@ -19,6 +19,9 @@ extern int g_fwd_split_q;     // nn_distance_fwd.cu
 extern int g_mma_cfg;         // nn_distance_fwd_mma.cu
 extern int g_mma_grid;        // nn_distance_fwd_mma.cu
 extern int g_bwd_split;       // nn_distance_bwd.cu
+extern int g_host_graph;         // host_api.cu
+extern int g_host_graph_chunks;  // host_api.cu
+extern int g_host_graph_epoch;   // host_api.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -35,6 +38,7 @@ int cuda_fail(cudaError_t e, const char* where) {
   return (int)e;
 }
 
+long long launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
 void note_kernel(const char* name) { t_last_kernel = name; }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -126,6 +130,16 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 9) {
     ga::g_bwd_split = value;
+    return GA_OK;
+  }
+  if (key == 10) {
+    ga::g_host_graph = value;
+    ga::g_host_graph_epoch++;
+    return GA_OK;
+  }
+  if (key == 11) {
+    ga::g_host_graph_chunks = value;
+    ga::g_host_graph_epoch++;
     return GA_OK;
   }
   ga::set_error("ga_set_tuning: unknown key %d", key);

@@ -14,6 +14,11 @@ struct Arena {
   int dev = -1;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second lane for chunked copy/compute overlap
+  // captured pipeline (ga_nn_distance_fwd_bwd_host): copy-out lane, one kernel lane per chunk, fork/join events
+  cudaStream_t out_lane = nullptr;
+  cudaStream_t k_lane[8] = {};
+  cudaEvent_t ev[48] = {};
+  unsigned long long generation = 0;  // bumped when `base` moves: cached graphs hold device addresses
   // deliberately no destructor: at process teardown the CUDA context may already be gone
 };
 static thread_local Arena t_arena;
@@ -26,6 +31,17 @@ static int arena_reserve(size_t bytes, char** base, cudaStream_t* st) {
     if (A.base) cudaFree(A.base);
     if (A.stream) cudaStreamDestroy(A.stream);
     if (A.stream2) cudaStreamDestroy(A.stream2);
+    if (A.out_lane) cudaStreamDestroy(A.out_lane);
+    A.out_lane = nullptr;
+    for (auto& k : A.k_lane) {
+      if (k) cudaStreamDestroy(k);
+      k = nullptr;
+    }
+    for (auto& e : A.ev) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+    }
+    A.generation++;
     A.base = nullptr;
     A.cap = 0;
     A.stream = nullptr;
@@ -45,6 +61,7 @@ static int arena_reserve(size_t bytes, char** base, cudaStream_t* st) {
     size_t want = bytes + (bytes >> 2) + (1u << 20);
     GA_CUDA_TRY(cudaMalloc(&A.base, want));
     A.cap = want;
+    A.generation++;
   }
   *base = A.base;
   *st = A.stream;
@@ -132,6 +149,157 @@ static bool device_can_touch(const void* p) {
     int _rc = (expr);            \
     if (_rc != GA_OK) return _rc; \
   } while (0)
+
+
+// ---- graph replay of the host fwd+bwd step -------------------------------------------------
+// The direct path below costs ~24 driver calls per step (10 copies and 2 kernels per chunk), about
+// as long on the CPU as the whole step takes on the GPU.  A training loop hands in the SAME pinned
+// buffers every step (src/adv_ae.py feeds fixed placeholders), so the second time a (shape,
+// pointers) key is seen the step is captured once as a CUDA graph and replayed from then on with
+// one cudaGraphLaunch.  The graph is laid out as a three-stage pipeline over chunks of the batch: H2D copies chained on one lane (chunk i's inputs arrive
+// before chunk i+1's start), each chunk's kernels on its own lane (free to overlap the tail of
+// the previous chunk), D2H copies chained on a third lane: dist/idx right after the forward,
+// gradients after the backward.  Pageable buffers never take this path.
+int g_host_graph = 0;         // tuning hook (key 10): 0 auto, 1 never replay, 2 capture on first sight
+int g_host_graph_chunks = 0;  // tuning hook (key 11): chunks of the captured pipeline (0 = auto)
+int g_host_graph_epoch = 0;   // bumped by ga_set_tuning(10 | 11): cached graphs of older epochs are dropped
+
+struct HostGraph {
+  cudaGraphExec_t exec = nullptr;
+  int dev = -1, b = 0, n = 0, m = 0, mode = 0, nchunk = 0, launches = 0, seen = 0;
+  bool failed = false;
+  const void* ptr[10] = {};
+  unsigned long long generation = 0, stamp = 0;
+  int epoch = 0;
+};
+static thread_local HostGraph t_graphs[4];
+static thread_local unsigned long long t_graph_clock = 0;
+long long launch_count_now();  // core.cu
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+struct FwdBwdBufs {
+  const float *xyz1, *xyz2, *gd1, *gd2;             // host in
+  float *dist1, *dist2, *gx1, *gx2;                 // host out
+  int *idx1, *idx2;
+  float *d_x1, *d_x2, *d_g1, *d_g2, *d_d1, *d_d2, *d_o1, *d_o2;  // arena
+  int *d_i1, *d_i2;
+};
+
+static int pipeline_lanes(int nchunk) {
+  Arena& A = t_arena;
+  if (!A.out_lane) GA_CUDA_TRY(cudaStreamCreateWithFlags(&A.out_lane, cudaStreamNonBlocking));
+  for (int i = 0; i < nchunk; i++)
+    if (!A.k_lane[i]) GA_CUDA_TRY(cudaStreamCreateWithFlags(&A.k_lane[i], cudaStreamNonBlocking));
+  for (auto& e : A.ev)
+    if (!e) GA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return GA_OK;
+}
+
+// Issue the pipeline on (A.stream = copy-in and origin, k lanes, out lane).  Used under capture.
+static int issue_pipeline(const FwdBwdBufs& f, int b, int n, int m, int mode, int nchunk) {
+  Arena& A = t_arena;
+  cudaStream_t sin = A.stream, sout = A.out_lane;
+  cudaEvent_t fork = A.ev[0], join = A.ev[1];
+  cudaEvent_t* ev_x = A.ev + 2;    // xyz of chunk ch on the device
+  cudaEvent_t* ev_g = A.ev + 10;   // upstream gradients of chunk ch on the device
+  cudaEvent_t* ev_f = A.ev + 18;   // forward of chunk ch done
+  cudaEvent_t* ev_b = A.ev + 26;   // backward of chunk ch done
+  GA_CUDA_TRY(cudaEventRecord(fork, sin));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sout, fork, 0));
+  for (int ch = 0; ch < nchunk; ch++) {
+    const int b0 = (int)((long long)b * ch / nchunk), b1 = (int)((long long)b * (ch + 1) / nchunk);
+    const int bc = b1 - b0;
+    cudaStream_t sk = A.k_lane[ch];
+    const size_t o1 = (size_t)b0 * n, o2 = (size_t)b0 * m, c1 = (size_t)bc * n, c2 = (size_t)bc * m;
+    GA_CUDA_TRY(cudaMemcpyAsync(f.d_x1 + o1 * 3, f.xyz1 + o1 * 3, c1 * 12, cudaMemcpyHostToDevice, sin));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.d_x2 + o2 * 3, f.xyz2 + o2 * 3, c2 * 12, cudaMemcpyHostToDevice, sin));
+    GA_CUDA_TRY(cudaEventRecord(ev_x[ch], sin));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.d_g1 + o1, f.gd1 + o1, c1 * 4, cudaMemcpyHostToDevice, sin));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.d_g2 + o2, f.gd2 + o2, c2 * 4, cudaMemcpyHostToDevice, sin));
+    GA_CUDA_TRY(cudaEventRecord(ev_g[ch], sin));
+
+    GA_CUDA_TRY(cudaStreamWaitEvent(sk, ev_x[ch], 0));
+    GA_TRY(ga_nn_distance_fwd(bc, n, m, f.d_x1 + o1 * 3, f.d_x2 + o2 * 3, f.d_d1 + o1, f.d_i1 + o1, f.d_d2 + o2,
+                              f.d_i2 + o2, mode, (ga_stream_t)sk));
+    GA_CUDA_TRY(cudaEventRecord(ev_f[ch], sk));
+    GA_CUDA_TRY(cudaStreamWaitEvent(sk, ev_g[ch], 0));
+    GA_TRY(ga_nn_distance_bwd(bc, n, m, f.d_x1 + o1 * 3, f.d_x2 + o2 * 3, f.d_g1 + o1, f.d_i1 + o1, f.d_g2 + o2,
+                              f.d_i2 + o2, f.d_o1 + o1 * 3, f.d_o2 + o2 * 3, (ga_stream_t)sk));
+    GA_CUDA_TRY(cudaEventRecord(ev_b[ch], sk));
+
+    GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_f[ch], 0));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.dist1 + o1, f.d_d1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.idx1 + o1, f.d_i1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.dist2 + o2, f.d_d2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.idx2 + o2, f.d_i2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
+    GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_b[ch], 0));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.gx1 + o1 * 3, f.d_o1 + o1 * 3, c1 * 12, cudaMemcpyDeviceToHost, sout));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.gx2 + o2 * 3, f.d_o2 + o2 * 3, c2 * 12, cudaMemcpyDeviceToHost, sout));
+  }
+  // every kernel lane ends in ev_b[ch], which the out lane waited for: joining the out lane joins all
+  GA_CUDA_TRY(cudaEventRecord(join, sout));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sin, join, 0));
+  return GA_OK;
+}
+
+static int capture_pipeline(HostGraph& G, const FwdBwdBufs& f, int b, int n, int m, int mode, int nchunk) {
+  GA_TRY(pipeline_lanes(nchunk));
+  cudaStream_t s0 = t_arena.stream;
+  const long long l0 = launch_count_now();
+  GA_CUDA_TRY(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+  const int rc = issue_pipeline(f, b, n, m, mode, nchunk);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(s0, &graph);
+  if (rc != GA_OK || e != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != GA_OK) return rc;
+    return cuda_fail(e != cudaSuccess ? e : cudaErrorUnknown, "cudaStreamEndCapture (host pipeline)");
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&G.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) {
+    G.exec = nullptr;
+    cudaGetLastError();
+    return cuda_fail(ei, "cudaGraphInstantiate (host pipeline)");
+  }
+  G.launches = (int)(launch_count_now() - l0);
+  count_launch(-G.launches);  // counted at capture, but nothing ran yet: replays count below
+  G.nchunk = nchunk;
+  return GA_OK;
+}
+
+// Returns the cache slot for this call (never null): a hit, or the least recently used slot re-keyed.
+static HostGraph& graph_slot(int dev, int b, int n, int m, int mode, const void* const (&ptr)[10]) {
+  Arena& A = t_arena;
+  HostGraph* lru = &t_graphs[0];
+  for (auto& G : t_graphs) {
+    bool same = G.seen > 0 && G.dev == dev && G.b == b && G.n == n && G.m == m && G.mode == mode &&
+                G.generation == A.generation && G.epoch == g_host_graph_epoch;
+    for (int i = 0; same && i < 10; i++) same = G.ptr[i] == ptr[i];
+    if (same) {
+      G.stamp = ++t_graph_clock;
+      return G;
+    }
+    if (G.stamp < lru->stamp) lru = &G;
+  }
+  if (lru->exec) cudaGraphExecDestroy(lru->exec);
+  *lru = HostGraph();
+  lru->dev = dev; lru->b = b; lru->n = n; lru->m = m; lru->mode = mode;
+  for (int i = 0; i < 10; i++) lru->ptr[i] = ptr[i];
+  lru->generation = A.generation;
+  lru->epoch = g_host_graph_epoch;
+  lru->stamp = ++t_graph_clock;
+  return *lru;
+}
 
 }  // namespace ga
 
@@ -256,6 +424,38 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
     GA_TRY(ga_nn_distance_bwd(b, n, m, d_x1, d_x2, d_g1, d_i1, d_g2, d_i2, grad_xyz1, grad_xyz2, (ga_stream_t)st));
     GA_CUDA_TRY(cudaStreamSynchronize(st));
     return GA_OK;
+  }
+  // Same pinned buffers as before: replay the captured pipeline (see HostGraph above).
+  if (g_host_graph != 1 && n > 0 && m > 0 && b >= 1) {
+    const void* const key[10] = {xyz1, xyz2, grad_dist1, grad_dist2, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2};
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    HostGraph& G = graph_slot(dev, b, n, m, mode, key);
+    G.seen++;
+    if (!G.failed && G.exec == nullptr && (G.seen >= 2 || g_host_graph == 2)) {
+      bool all_pinned = true;
+      for (int i = 0; all_pinned && i < 10; i++) all_pinned = is_pinned(key[i]);
+      G.failed = !all_pinned;
+      if (all_pinned) {
+        // Measured on the B200 box (profiles/r01_tune_e2e.json, B x 2048 x 2048): every extra chunk
+        // costs ~25 us of dependency hops between copy and compute nodes, so the overlap only pays
+        // once: B=10 one chunk 93 us (direct path 113), B=50 two chunks 210 us (direct 239, one chunk
+        // 219, three 224, eight 350), B=200 two chunks 575 us (direct 611).
+        const size_t traffic = (e1 + e2) * 36;
+        int nc = g_host_graph_chunks > 0 ? g_host_graph_chunks : (traffic >= ((size_t)4 << 20) ? 2 : 1);
+        nc = nc < 1 ? 1 : (nc > 8 ? 8 : nc);
+        if (nc > b) nc = b;
+        FwdBwdBufs f = {xyz1, xyz2, grad_dist1, grad_dist2, dist1, dist2, grad_xyz1, grad_xyz2, idx1, idx2,
+                        d_x1, d_x2, d_g1, d_g2, d_d1, d_d2, d_o1, d_o2, d_i1, d_i2};
+        if (capture_pipeline(G, f, b, n, m, mode, nc) != GA_OK) G.failed = true;  // fall through to the direct path
+      }
+    }
+    if (G.exec != nullptr) {
+      GA_CUDA_TRY(cudaGraphLaunch(G.exec, st));
+      count_launch(G.launches);
+      GA_CUDA_TRY(cudaStreamSynchronize(st));
+      return GA_OK;
+    }
   }
   // Batch elements are independent: split the batch into chunks that alternate between two
   // streams, so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 run under the kernels

@@ -254,6 +254,57 @@ def test_fwd_bwd_host_entry_point(ga, pinned, path):
     lib.ga_set_tuning(2, 0)
 
 
+@pytest.mark.parametrize("chunks", [0, 1, 3, 8])
+def test_fwd_bwd_host_graph_replay(ga, chunks):
+    """The captured pipeline of ga_nn_distance_fwd_bwd_host: the same pinned buffers come back with
+    NEW contents every step (a training loop), the replayed graph must give the fresh results; a
+    different buffer set, a different shape and pageable buffers in between must not disturb it."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    p = ctypes.c_void_p
+    lib.ga_set_tuning(11, chunks)
+    launches = []
+    try:
+        def buffers(b, n, m, pin=True):
+            f = (lambda x: x.pin_memory()) if pin else (lambda x: x)
+            return [f(torch.empty(b, n, 3)), f(torch.empty(b, m, 3)), f(torch.empty(b, n)), f(torch.empty(b, m)),
+                    f(torch.empty(b, n)), f(torch.empty(b, n, dtype=torch.int32)), f(torch.empty(b, m)),
+                    f(torch.empty(b, m, dtype=torch.int32)), f(torch.empty(b, n, 3)), f(torch.empty(b, m, 3))]
+
+        def step(buf, b, n, m, seed):
+            a, c = cloud(seed, (b, n, 3)), cloud(seed + 1, (b, m, 3))
+            gd1 = np.random.default_rng(seed).standard_normal((b, n)).astype(np.float32)
+            gd2 = np.random.default_rng(seed + 1).standard_normal((b, m)).astype(np.float32)
+            for dst, src in zip(buf[:4], (a, c, gd1, gd2)):
+                dst.copy_(torch.from_numpy(src))
+            for o in buf[4:]:
+                o.zero_()
+            l0 = ga.launch_count()
+            _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, *[p(x.data_ptr()) for x in buf], 0))
+            launches.append(ga.launch_count() - l0)
+            dev = ga.nn_distance(t(a), t(c))
+            g = ga.nn_distance_grad(t(a), t(c), t(gd1), dev[1], t(gd2), dev[3])
+            for x, y in zip(buf[4:], tuple(dev) + tuple(g)):
+                assert bits_equal(x.numpy(), y.cpu().numpy()), (b, n, m, seed, chunks)
+
+        b, n, m = 24, 2048, 2000
+        main, other, pageable = buffers(b, n, m), buffers(b, n, m), buffers(b, n, m, pin=False)
+        small = buffers(3, 300, 257)
+        for it in range(4):          # step 0 direct, step 1 captures, steps 2.. replay
+            step(main, b, n, m, 500 + 10 * it)
+        assert all(x >= 2 for x in launches), launches   # replays keep counting the kernels they run
+        step(other, b, n, m, 600)
+        step(small, 3, 300, 257, 610)
+        step(pageable, b, n, m, 620)
+        step(pageable, b, n, m, 630)
+        for it in range(3):
+            step(main, b, n, m, 700 + 10 * it)
+            step(other, b, n, m, 800 + 10 * it)
+            step(small, 3, 300, 257, 900 + 10 * it)
+    finally:
+        lib.ga_set_tuning(11, 0)
+
+
 # ------------------------------------------------------------------ backward
 def check_bwd(ga, oracle, a, b, gd1, i1, gd2, i2):
     """Both launch shapes of the gradient kernel: one CTA per cloud, and output points split over 4 CTAs."""

@@ -15,7 +15,7 @@ for rep in sorted(os.listdir(G)):
         if len(rows) >= 3:
             h, v = rows[0], rows[2]
             d = dict(zip(h, v))
-            kn = d.get("Kernel Name", "").split("(")[0].split("<")[0].split("::")[-1]
+            kn = d.get("Kernel Name", "").split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
             if kn.startswith("nn_fwd") and "_fwd" in rep:
                 def mb(x):
                     return float(d[x]) * 1e6 if d.get(x) else 0.0

@@ -1,0 +1,49 @@
+"""Wall-clock timing of ga_nn_distance_fwd_bwd_host (the e2e leg of bench.py): direct two-lane path
+vs the replayed CUDA-graph pipeline with 1..8 chunks.  Development tool; writes gpurun_out/tune_e2e.json."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from geometric_adv_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+p = ctypes.c_void_p
+out = {}
+for (B, N, M) in [(50, 2048, 2048), (10, 2048, 2048), (200, 2048, 2048)]:
+    rng = np.random.default_rng(0)
+    mk = lambda *s: torch.from_numpy((rng.random(s, dtype=np.float32) - 0.5).astype(np.float32)).pin_memory()
+    bufs = [mk(B, N, 3), mk(B, M, 3), mk(B, N), mk(B, M), torch.empty(B, N).pin_memory(),
+            torch.empty(B, N, dtype=torch.int32).pin_memory(), torch.empty(B, M).pin_memory(),
+            torch.empty(B, M, dtype=torch.int32).pin_memory(), torch.empty(B, N, 3).pin_memory(),
+            torch.empty(B, M, 3).pin_memory()]
+    args = [p(x.data_ptr()) for x in bufs]
+
+    def step():
+        _lib.check(lib.ga_nn_distance_fwd_bwd_host(B, N, M, *args, 0))
+
+    key = "b%d" % B
+    out[key] = {}
+    for name, k10, k11 in [("direct", 1, 0)] + [("graph_c%d" % c, 0, c) for c in (1, 2, 3, 4, 5, 6, 8)] + [("graph_auto", 0, 0)]:
+        lib.ga_set_tuning(10, k10)
+        lib.ga_set_tuning(11, k11)
+        for _ in range(5):
+            step()
+        ts = []
+        for _ in range(60):
+            t0 = time.perf_counter()
+            step()
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        out[key][name] = {"min_us": ts[0] * 1e6, "med_us": ts[len(ts) // 2] * 1e6}
+        print(key, name, "min %.1f us  med %.1f us" % (ts[0] * 1e6, ts[len(ts) // 2] * 1e6), flush=True)
+    lib.ga_set_tuning(10, 0)
+    lib.ga_set_tuning(11, 0)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune_e2e.json"), "w"), indent=1)
