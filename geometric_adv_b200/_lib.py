@@ -51,6 +51,7 @@ SIGNATURES = {
     "ga_probe_fp32_peak": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p]),
     "ga_probe_launch_floor": (_i, [_i, C.POINTER(C.c_float), _p]),
     "ga_debug_mma_filter": (_i, [_i, _i, _p, _p, _p, _p]),
+    "ga_debug_umma_filter": (_i, [_i, _i, _p, _p, _p, _p]),
 }
 
 

@@ -239,15 +239,15 @@ __device__ __forceinline__ unsigned tile_candidate_mask(const float4* __restrict
 //  2. second tiles are rare (a few per warp): the whole warp evaluates such a tile exactly, one
 //     target per lane, and merges by (value, index);
 //  3. cnt > 2 / many candidates / non-finite window: warp_exact_scan (nn_search.cuh).
-template <int MODE>
-__device__ __forceinline__ void refine_tiles(QueryState<2>& s, const float4* __restrict__ tgt, int c0, int nt,
-                                             int ntile, const int (&cnt)[2], const int (&ta)[2], const int (&tb)[2],
-                                             const float (&thr)[2]) {
+template <int MODE, int Q = 2>
+__device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __restrict__ tgt, int c0, int nt,
+                                             int ntile, const int (&cnt)[Q], const int (&ta)[Q], const int (&tb)[Q],
+                                             const float (&thr)[Q]) {
   constexpr int T = kMmaT;
   const int lane = threadIdx.x & 31;
-  bool hard[2], second[2];
+  bool hard[Q], second[Q];
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
+  for (int j = 0; j < Q; j++) {
     hard[j] = s.valid[j] && cnt[j] > 2;
     second[j] = s.valid[j] && cnt[j] == 2;
     unsigned mask = 0;
@@ -269,7 +269,7 @@ __device__ __forceinline__ void refine_tiles(QueryState<2>& s, const float4* __r
     }
   }
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
+  for (int j = 0; j < Q; j++) {
     unsigned pending = __ballot_sync(0xffffffffu, second[j]);
     while (pending) {
       const int src = __ffs(pending) - 1;
@@ -304,7 +304,7 @@ __device__ __forceinline__ void refine_tiles(QueryState<2>& s, const float4* __r
     }
   }
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
+  for (int j = 0; j < Q; j++) {
     unsigned pending = __ballot_sync(0xffffffffu, hard[j]);
     while (pending) {
       const int src = __ffs(pending) - 1;

@@ -177,6 +177,8 @@ const char* ga_last_kernel(void);
  * h(q,t) ~ |t|^2 - 2 q.t of one cloud pair, out[q*m + t], n queries (xyz1), m <= 2048 targets
  * (xyz2), device pointers.  Tests compare it with the fp64 value against the documented bound. */
 int ga_debug_mma_filter(int n, int m, const float* xyz1, const float* xyz2, float* out, ga_stream_t stream);
+/* Same evidence for the tcgen05 / TMEM filter (forward variant 22, nn_distance_fwd_umma.cu). */
+int ga_debug_umma_filter(int n, int m, const float* xyz1, const float* xyz2, float* out, ga_stream_t stream);
 
 #ifdef __cplusplus
 }
