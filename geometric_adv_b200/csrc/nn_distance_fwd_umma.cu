@@ -13,10 +13,15 @@
 // the caller's fp32 xyz, so no TMA descriptor is involved.
 //
 // One tcgen05.mma (M=128 queries = TMEM lanes, N=256 targets = TMEM columns, K=16) produces
-// 32768 filter values in ~128 clocks; 16 warps drain them with tcgen05.ld.32x32b (thread = one
-// query row, 32 consecutive columns = one refine tile) and fold each tile into a key (tile minimum
-// with the tile number in its 4 low mantissa bits) with FMNMX3, keeping the three smallest keys.
-// The 512 TMEM columns hold two accumulator buffers: MMA s+1 runs while step s is drained.
+// 32768 filter values in ~128 clocks.  The 512 TMEM columns hold two accumulator buffers.  A
+// dedicated warp issues the MMAs; 16 warps drain: a thread owns one query row and 64 columns, reads
+// them with two tcgen05.ld.32x32b.x32 (32 consecutive columns = one refine tile) and folds each tile
+// into a key (tile minimum with a 4-bit tile number in the low mantissa bits) with FMNMX3, keeping
+// the three smallest keys.  mbarriers pair the roles: tcgen05.commit -> full[b] -> drain,
+// drain -> empty[b] -> issuer; a buffer is handed back as soon as its values sit in registers.
+// Measured with clock64 stamps (tools/umma_trace.py): an MMA is visible to the drain warps ~130
+// cycles after its issue, so two buffers suffice; what limits the pipeline is the instruction count
+// of the issuer loop (its warp gets one issue slot in five), hence the A rows are built by drain warps.
 //
 // Work decomposition: persistent, one CTA per SM.  All (batch, direction, 128-query M-tile) jobs
 // are cut into equal contiguous shares; a share is walked in segments of one target cloud, which
@@ -31,6 +36,8 @@ namespace ga {
 
 constexpr int kUmmaM = 128;        // queries per MMA (TMEM lanes)
 constexpr int kUmmaN = 256;        // targets per MMA (TMEM columns of one accumulator buffer)
+constexpr int kUmmaBufs = 2;       // accumulator buffers: 2 x 256 = the 512 TMEM columns
+constexpr int kUmmaABufs = 4;      // ring of A operands: job jl+2 is built while job jl is drained
 constexpr int kUmmaCH = 2048;      // targets of a segment
 constexpr int kUmmaWarps = 16;
 constexpr int kUmmaThreads = kUmmaWarps * 32;
@@ -41,10 +48,10 @@ constexpr int kUmmaT = kMmaT;      // refine tile
 constexpr size_t kUmmaOffTgt = 0;                                                  // pair-SoA + pipeline pad
 constexpr size_t kUmmaOffRed = kUmmaOffTgt + (size_t)kUmmaCH * 16 + (size_t)kPipeU * 32;  // red[32]
 constexpr size_t kUmmaOffB = kUmmaOffRed + 128;                                    // B operand, 32 B per target
-constexpr size_t kUmmaOffA = kUmmaOffB + (size_t)kUmmaCH * 32;                     // A operand, 2 x 128 rows
-constexpr size_t kUmmaOffKeys = kUmmaOffA + 2 * (size_t)kUmmaM * 32;               // [job][3][4][128] float
-constexpr size_t kUmmaOffBar = kUmmaOffKeys + (size_t)kUmmaMaxJobs * 3 * 4 * kUmmaM * 4;  // full[2], tmem base
-constexpr size_t kUmmaSmem = kUmmaOffBar + 32;
+constexpr size_t kUmmaOffA = kUmmaOffB + (size_t)kUmmaCH * 32;                     // A operand ring, 4 x 128 rows
+constexpr size_t kUmmaOffKeys = kUmmaOffA + kUmmaABufs * (size_t)kUmmaM * 32;               // [job][3][4][128] float
+constexpr size_t kUmmaOffBar = kUmmaOffKeys + (size_t)kUmmaMaxJobs * 3 * 4 * kUmmaM * 4;  // full[4], empty[4], tmem base
+constexpr size_t kUmmaSmem = kUmmaOffBar + 80;
 static_assert(kUmmaOffB % 128 == 0 && kUmmaOffA % 128 == 0 && kUmmaOffBar % 8 == 0, "operand alignment");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,6 +65,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
          (1ull << 46);
 }
 // Instruction descriptor: D fp32, A and B bf16, both K-major, N=256, M=128.
+// (N >> 3 in bits 17-22, M >> 4 in bits 24-28)
 constexpr uint32_t kUmmaIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) |
                                 ((uint32_t)(kUmmaM >> 4) << 24);
 
@@ -79,6 +87,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 // Bounded spin: a completion that never comes (a malformed descriptor) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
   for (int spin = 0; spin < (1 << 22); spin++) {
     uint32_t done;
     asm volatile(
@@ -158,20 +167,47 @@ __device__ __forceinline__ void umma_b_row(unsigned char* __restrict__ bop, cons
 }
 
 // Fold one 32-target tile (32 TMEM columns of this thread's row) into the three smallest keys.
+// Four independent FMNMX3 chains: a dependent FMNMX3 costs far more than its 2 issue cycles, and a
+// scheduler has only four drain warps to interleave.
 __device__ __forceinline__ void umma_fold(const float (&v)[32], int local_tile, float& c1, float& c2, float& c3) {
-  float m = fmin3(v[0], v[1], v[2]);
-#pragma unroll
-  for (int e = 3; e < 31; e += 2) m = fmin3(m, v[e], v[e + 1]);
-  m = fminf(m, v[31]);
+  float m0 = fmin3(v[0], v[1], v[2]), m1 = fmin3(v[8], v[9], v[10]);
+  float m2 = fmin3(v[16], v[17], v[18]), m3 = fmin3(v[24], v[25], v[26]);
+  m0 = fmin3(m0, v[3], v[4]);
+  m1 = fmin3(m1, v[11], v[12]);
+  m2 = fmin3(m2, v[19], v[20]);
+  m3 = fmin3(m3, v[27], v[28]);
+  m0 = fmin3(m0, v[5], v[6]);
+  m1 = fmin3(m1, v[13], v[14]);
+  m2 = fmin3(m2, v[21], v[22]);
+  m3 = fmin3(m3, v[29], v[30]);
+  m0 = fmin3(m0, v[7], m1);
+  m2 = fmin3(m2, v[23], m3);
+  const float m = fmin3(fmin3(m0, v[15], v[31]), m2, m2);
   const float key = __int_as_float((__float_as_int(m) & ~15) | local_tile);
   c3 = fminf(c3, fmaxf(c2, key));
   c2 = fminf(c2, fmaxf(c1, key));
   c1 = fminf(c1, key);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kUmmaThreads, 1) nn_fwd_umma_kernel(const FwdArgs a, const int mt1, const int mt2,
-                                                                    const long long J) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// TRACE (development, ga_debug_umma_trace): CTA 0 records clock64() stamps of its pipeline events.
+// trace[role * 4096 + 2 * i + {0, 1}], role 0 = issuer (empty wait done, MMA issued), role 1 = drain warp 0
+// lane 0 (full wait start, full wait done), role 3 = phases of a
+// segment (start, staged, scanned, refined).
+#define UMMA_STAMP(role, idx, which)                                                           \
+  do {                                                                                         \
+    if (TRACE && blockIdx.x == 0 && (idx) < 2048) trace[(role) * 4096 + 2 * (idx) + (which)] = clock64(); \
+  } while (0)
+
+// 17 warps: one scheduler holds 5 of them, 16384 / (5 * 32) = 102 registers per thread at most
+template <int MODE, bool TRACE = false>
+__global__ void __launch_bounds__(kUmmaThreads + 32, 1) nn_fwd_umma_kernel(const FwdArgs a, const int mt1,
+                                                                         const int mt2, const long long J,
+                                                                         long long* __restrict__ trace) {
+  constexpr int THREADS = kUmmaThreads + 32;  // 16 drain warps + the MMA issuer warp
   extern __shared__ __align__(128) unsigned char smem[];
   float4* tgt = reinterpret_cast<float4*>(smem + kUmmaOffTgt);
   float* red = reinterpret_cast<float*>(smem + kUmmaOffRed);
@@ -179,22 +215,34 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) nn_fwd_umma_kernel(const FwdA
   unsigned char* aop = smem + kUmmaOffA;
   float* keys = reinterpret_cast<float*>(smem + kUmmaOffKeys);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kUmmaOffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kUmmaOffBar + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kUmmaOffBar + 64);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int quad = warp & 3;   // TMEM lane quadrant this warp may read
-  const int slot = warp >> 2;  // 64-column slice of an accumulator buffer
+  const bool issuer = warp == kUmmaWarps;
+  const int quad = warp & 3;         // TMEM lane quadrant this warp may read
+  const int slot = (warp >> 2) & 3;  // 64-column quarter of a 256-column accumulator buffer
   const int row = quad * 32 + lane;
-  const uint32_t full0 = smem_u32(bars), full1 = smem_u32(bars + 1);
+  // full[b]: accumulator buffer b written (tcgen05.commit); empty[b]: its values sit in the registers of
+  // all 16 drain warps
+  const uint32_t full_base = smem_u32(bars), empty_base = smem_u32(bars + kUmmaBufs);
+  auto full = [&](unsigned b) { return full_base + 8u * b; };
+  auto empty = [&](unsigned b) { return empty_base + 8u * b; };
 
   if (tid == 0) {
-    mbar_init(full0, 1);
-    mbar_init(full1, 1);
+    for (int b = 0; b < kUmmaBufs; b++) {
+      mbar_init(full(b), 1);
+      mbar_init(empty(b), kUmmaWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t tmem = umma_tmem_alloc(tmem_slot, warp);  // contains a __syncthreads
   const uint32_t tmem_row = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * 64);
-  uint32_t phase0 = 0, phase1 = 0;  // parity of the next completion of full0 / full1
+  // Steps are numbered g = 0, 1, 2, ... over the whole kernel (gbase = first step of the segment, the
+  // same in every thread).  Step g uses buffer g & 1; its full barrier completes with parity
+  // (g >> 1) & 1, and before the issuer overwrites the buffer it needs the empty barrier of step g - 2
+  // (parity ((g >> 1) - 1) & 1).
+  unsigned gbase = 0;
+  int nseg = 0;
 
   const long long jpb = (long long)mt1 + mt2;
   const long long j0 = J * blockIdx.x / gridDim.x, j1 = J * (blockIdx.x + 1) / gridDim.x;
@@ -216,69 +264,111 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) nn_fwd_umma_kernel(const FwdA
     const int ntile = (nt + kUmmaT - 1) / kUmmaT;
     const int nblk = (nt + kUmmaN - 1) / kUmmaN;  // MMAs per job (>= 2)
 
-    const float bm = stage_targets<kUmmaThreads, kUmmaT>(tgt, red, tpts, 0, nt, ntile, tid);
-    for (int tau = tid; tau < nblk * kUmmaN; tau += kUmmaThreads) umma_b_row(bop, tgt, tau, nt);
-    auto stage_a = [&](int jl) {  // threads 0..127: one query row each
-      const int qi = (ml0 + jl) * kUmmaM + tid;
-      const bool ok = qi < nq;
-      const int qs = ok ? qi : 0;
-      umma_a_row(aop + (size_t)(jl & 1) * kUmmaM * 32, tid, __ldg(qpts + (size_t)qs * 3),
-                 __ldg(qpts + (size_t)qs * 3 + 1), __ldg(qpts + (size_t)qs * 3 + 2), ok);
+    if (tid == 0) UMMA_STAMP(3, 2 * nseg, 0);
+    const float bm = stage_targets<THREADS, kUmmaT>(tgt, red, tpts, 0, nt, ntile, tid);
+    for (int tau = tid; tau < nblk * kUmmaN; tau += THREADS) umma_b_row(bop, tgt, tau, nt);
+    // A rows of job jl (ring slot jl & 3): query (ml0 + jl) * 128 + rw
+    auto a_row = [&](int jl, int rw, float qx, float qy, float qz) {
+      umma_a_row(aop + (size_t)(jl & (kUmmaABufs - 1)) * kUmmaM * 32, rw, qx, qy, qz, (ml0 + jl) * kUmmaM + rw < nq);
     };
-    if (tid < kUmmaM) stage_a(0);
+    auto a_query = [&](int jl, int rw) {  // clamped index of that query
+      const int qi = (ml0 + jl) * kUmmaM + rw;
+      return qi < nq ? qi : 0;
+    };
+    if (tid < 2 * kUmmaM && (tid >> 7) < nj) {  // the first two jobs; later ones are built by the drain warps
+      const int qs = a_query(tid >> 7, tid & 127);
+      a_row(tid >> 7, tid & 127, __ldg(qpts + (size_t)qs * 3), __ldg(qpts + (size_t)qs * 3 + 1),
+            __ldg(qpts + (size_t)qs * 3 + 2));
+    }
     proxy_fence();
     __syncthreads();
+    if (tid == 0) UMMA_STAMP(3, 2 * nseg, 1);
 
     const int S = nj * nblk;
-    auto issue = [&](int s) {  // one thread: MMA of step s into buffer s & 1
-      const int jl = s / nblk, t = s - jl * nblk;
-      tc_fence_after();
-      umma_issue(tmem + (uint32_t)((s & 1) * kUmmaN), umma_desc(smem_u32(aop + (size_t)(jl & 1) * kUmmaM * 32)),
-                 umma_desc(smem_u32(bop + (size_t)t * kUmmaN * 32)));
-      umma_commit((s & 1) ? full1 : full0);
-    };
-    if (tid == 0) issue(0);
-
-    float c1 = kMmaBig, c2 = kMmaBig, c3 = kMmaBig;
-    int jl = 0, t = 0;
-    for (int s = 0; s < S; s++) {
-      if (tid == 0 && s + 1 < S) issue(s + 1);
-      // the A rows of the next job: its first MMA is issued at the top of step (jl+1)*nblk - 1 > s
-      if (t == 0 && jl + 1 < nj && tid < kUmmaM) {
-        stage_a(jl + 1);
-        proxy_fence();
+    if (issuer) {
+      // ---- MMA issuer warp: nothing but wait / issue / commit (every instruction of this loop is on
+      //      the critical path of the pipeline: the warp shares its scheduler with four drain warps)
+      const uint32_t desc_hi = (uint32_t)(256 >> 4) | (1u << 14);  // SBO, descriptor version (bits 32.., 46)
+      const uint32_t a_lo = ((smem_u32(aop) & 0x3ffffu) >> 4) | ((uint32_t)(128 >> 4) << 16);
+      const uint32_t b_lo = ((smem_u32(bop) & 0x3ffffu) >> 4) | ((uint32_t)(128 >> 4) << 16);
+      int jl = 0, t = 0;
+      for (int s = 0; s < S; s++) {
+        const unsigned g = gbase + s, b = g & 1;
+        if (g >= kUmmaBufs) mbar_wait(empty(b), ((g >> 1) - 1) & 1);
+        tc_fence_after();
+        UMMA_STAMP(0, g, 0);
+        const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)(jl & (kUmmaABufs - 1)) * (kUmmaM * 32 / 16));
+        const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)t * (kUmmaN * 32 / 16));
+        if (lane == 0) {
+          umma_issue(tmem + b * kUmmaN, adesc, bdesc);
+          umma_commit(full(b));
+        }
+        __syncwarp();
+        UMMA_STAMP(0, g, 1);
+        if (++t == nblk) {
+          t = 0;
+          jl++;
+        }
       }
-      if (s & 1) {
-        mbar_wait(full1, phase1);
-        phase1 ^= 1;
-      } else {
-        mbar_wait(full0, phase0);
-        phase0 ^= 1;
-      }
-      tc_fence_after();
+    } else {
+      // ---- drain warps: thread = (query row, 64-column quarter).  Two 32-column tiles per step; the
+      //      TMEM load of the next tile is in flight while the current one is folded, and the buffer is
+      //      handed back as soon as both tiles are in registers.  Warps 0-3 (one thread per row) also
+      //      build the A rows of job jl + 2: coordinates loaded at the job's first step, row written at
+      //      its second; the issuer reads them only after it has seen the empty barrier of a later
+      //      step, which every warp arrives at after this point in program order.
+      float c1 = kMmaBig, c2 = kMmaBig, c3 = kMmaBig;
+      int jl = 0, t = 0;
+      float v[32], w[32];
+      float nx = 0.0f, ny = 0.0f, nz = 0.0f;
       {
-        float v[32], w[32];
-        const uint32_t ta = tmem_row + (uint32_t)((s & 1) * kUmmaN);
-        tmem_ld32(ta, v);
-        tmem_ld32(ta + 32, w);
+        const unsigned g = gbase;
+        mbar_wait(full(g & 1), (g >> 1) & 1);
+        tc_fence_after();
+        tmem_ld32(tmem_row + (g & 1) * kUmmaN, v);
         tmem_ld_wait();
+      }
+      for (int s = 0; s < S; s++) {
+        const unsigned g = gbase + s, b = g & 1;
+        tmem_ld32(tmem_row + b * kUmmaN + 32, w);
+        if (slot == 0 && jl + 2 < nj) {
+          if (t == 0) {
+            const int qs = a_query(jl + 2, row);
+            nx = __ldg(qpts + (size_t)qs * 3);
+            ny = __ldg(qpts + (size_t)qs * 3 + 1);
+            nz = __ldg(qpts + (size_t)qs * 3 + 2);
+          } else if (t == 1) {
+            a_row(jl + 2, row, nx, ny, nz);
+            proxy_fence();
+          }
+        }
         umma_fold(v, 2 * t, c1, c2, c3);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty(b));
+        if (s + 1 < S) {
+          if (lane == 0 && warp == 0) UMMA_STAMP(1, g + 1, 0);
+          mbar_wait(full(b ^ 1), ((g + 1) >> 1) & 1);
+          if (lane == 0 && warp == 0) UMMA_STAMP(1, g + 1, 1);
+          tc_fence_after();
+          tmem_ld32(tmem_row + (b ^ 1) * kUmmaN, v);
+        }
         umma_fold(w, 2 * t + 1, c1, c2, c3);
+        tmem_ld_wait();
+        if (++t == nblk) {  // job finished: publish this thread's keys, reset
+          float* kq = keys + (size_t)jl * (3 * 4 * kUmmaM) + slot * kUmmaM + row;
+          kq[0] = c1;
+          kq[4 * kUmmaM] = c2;
+          kq[8 * kUmmaM] = c3;
+          c1 = c2 = c3 = kMmaBig;
+          t = 0;
+          jl++;
+        }
       }
-      if (t == nblk - 1) {  // job finished: publish this thread's keys, reset
-        float* kq = keys + (size_t)jl * (3 * 4 * kUmmaM) + slot * kUmmaM + row;
-        kq[0] = c1;
-        kq[4 * kUmmaM] = c2;
-        kq[8 * kUmmaM] = c3;
-        c1 = c2 = c3 = kMmaBig;
-        jl++;
-        t = 0;
-      } else {
-        t++;
-      }
-      tc_fence_before();
-      __syncthreads();  // buffer s & 1 is drained: MMA s + 2 may overwrite it
     }
+    __syncthreads();  // keys of the whole segment are published
+    if (tid == 0) UMMA_STAMP(3, 2 * nseg + 1, 0);
 
     // ---- refine: one query per thread and pass ---------------------------------------------
     const float t0x = __ldg(tpts), t0y = __ldg(tpts + 1), t0z = __ldg(tpts + 2);
@@ -286,7 +376,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) nn_fwd_umma_kernel(const FwdA
     int* oidx = (rev ? a.idx2 : a.idx1) + (size_t)batch * nq;
     float* mdist = rev ? a.mdist2 : a.mdist1;
     int* midx = rev ? a.midx2 : a.midx1;
-    for (int base = 0; base < nj * kUmmaM; base += kUmmaThreads) {
+    for (int base = 0; base < nj * kUmmaM && !issuer; base += kUmmaThreads) {
       const int ql = base + tid;                  // query within the segment
       const int qi = ml0 * kUmmaM + ql;           // query within its cloud
       QueryState<1> qs;
@@ -347,7 +437,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) nn_fwd_umma_kernel(const FwdA
         }
       }
     }
+    if (tid == 0) UMMA_STAMP(3, 2 * nseg + 1, 1);
+    nseg++;
     j = pend;
+    gbase += (unsigned)S;
     // the next segment's stage_targets starts with a __syncthreads: tgt / keys are free by then
   }
   umma_tmem_free(tmem, warp);
@@ -363,7 +456,7 @@ __global__ void __launch_bounds__(128) umma_filter_dump_kernel(int n, int m, con
   unsigned char* bop = smem + kUmmaOffB;
   unsigned char* aop = smem + kUmmaOffA;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kUmmaOffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kUmmaOffBar + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kUmmaOffBar + 64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t full0 = smem_u32(bars);
   if (tid == 0) {
@@ -409,7 +502,7 @@ int g_umma_grid = 0;  // tuning hook (key 12): CTAs of the tcgen05 kernel (0 = o
 
 bool fwd_umma_supported(int n, int m) { return n > kUmmaN && m > kUmmaN && n <= kUmmaCH && m <= kUmmaCH; }
 
-int launch_fwd_umma(const FwdArgs& a, int mode, cudaStream_t st) {
+static int launch_fwd_umma_impl(const FwdArgs& a, int mode, cudaStream_t st, long long* trace) {
   if (!fwd_umma_supported(a.n, a.m)) {
     set_error("nn_fwd_umma_kernel: clouds of %d..%d points", kUmmaN + 1, kUmmaCH);
     return GA_ERR_UNSUPPORTED;
@@ -417,22 +510,27 @@ int launch_fwd_umma(const FwdArgs& a, int mode, cudaStream_t st) {
   const int mt1 = (a.n + kUmmaM - 1) / kUmmaM, mt2 = (a.m + kUmmaM - 1) / kUmmaM;
   const long long J = (long long)a.b * (mt1 + mt2);
   if (J <= 0) return GA_OK;
-  auto k = mode == GA_MODE_CPU_EXACT ? nn_fwd_umma_kernel<GA_MODE_CPU_EXACT> : nn_fwd_umma_kernel<GA_MODE_GPU_REF>;
+  auto k = trace != nullptr ? nn_fwd_umma_kernel<GA_MODE_CPU_EXACT, true>
+                            : (mode == GA_MODE_CPU_EXACT ? nn_fwd_umma_kernel<GA_MODE_CPU_EXACT, false>
+                                                         : nn_fwd_umma_kernel<GA_MODE_GPU_REF, false>);
   {
-    static std::atomic<unsigned> done_mask[2];
+    static std::atomic<unsigned> done_mask[3];
+    const int slot = trace != nullptr ? 2 : mode;
     int dev = 0;
     GA_CUDA_TRY(cudaGetDevice(&dev));
-    if (!(done_mask[mode].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+    if (!(done_mask[slot].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
       GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
-      done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+      done_mask[slot].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
     }
   }
   long long grid = g_umma_grid > 0 ? g_umma_grid : sm_count();
   if (grid > J) grid = J;
-  k<<<(unsigned)grid, kUmmaThreads, kUmmaSmem, st>>>(a, mt1, mt2, J);
+  k<<<(unsigned)grid, kUmmaThreads + 32, kUmmaSmem, st>>>(a, mt1, mt2, J, trace);
   GA_LAUNCH_CHECK("nn_fwd_umma_kernel");
   return GA_OK;
 }
+
+int launch_fwd_umma(const FwdArgs& a, int mode, cudaStream_t st) { return launch_fwd_umma_impl(a, mode, st, nullptr); }
 
 }  // namespace ga
 
@@ -448,4 +546,17 @@ extern "C" int ga_debug_umma_filter(int n, int m, const float* xyz1, const float
   k<<<(n + ga::kUmmaM - 1) / ga::kUmmaM, 128, ga::kUmmaSmem, st>>>(n, m, xyz1, xyz2, out);
   GA_LAUNCH_CHECK("umma_filter_dump_kernel");
   return GA_OK;
+}
+
+// Development: one traced run of the tcgen05 kernel (mode 0); `trace` = 4 * 4096 int64 on the device.
+extern "C" int ga_debug_umma_trace(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist1, int* idx1,
+                                   float* dist2, int* idx2, long long* trace, ga_stream_t stream) {
+  ga::FwdArgs a;
+  a.b = b; a.n = n; a.m = m;
+  a.xyz1 = xyz1; a.xyz2 = xyz2;
+  a.dist1 = dist1; a.idx1 = idx1; a.dist2 = dist2; a.idx2 = idx2;
+  a.tiles1 = a.tiles2 = 0;
+  a.mdist1 = a.mdist2 = nullptr;
+  a.midx1 = a.midx2 = nullptr;
+  return ga::launch_fwd_umma_impl(a, GA_MODE_CPU_EXACT, ga::as_stream(stream), trace);
 }

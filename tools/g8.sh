@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_umma_filter_gpu.py -m gpu -x -q > gpurun_out/pytest_umma.log 2>&1; echo "umma tests rc=$?"; tail -3 gpurun_out/pytest_umma.log
+timeout 300 python tools/tune_mma.py > gpurun_out/tune_mma.log 2>&1; grep -E "mma_cfg5|umma" gpurun_out/tune_mma.log
