@@ -40,12 +40,18 @@ struct BwdArgs {
   float* gxyz2;
 };
 
-// smem: cnt[W][K] u16 | total[K] i32 | start[K] i32 | wsum[W] i32 | order[L] u16
+// Partner clouds up to this size are staged in shared memory ({x, y, z, grad_dist} per point): the
+// contributor walk is a chain of dependent gathers, ~30 cycles per hop from shared memory instead
+// of one L2 round trip (~700 cycles) per hop from global memory.
+constexpr int kBwdStageMax = 4096;
+
+// smem: cnt[W][K] u16 | total[K] i32 | start[K] i32 | wsum[W] i32 | order[L] u16 | partner[L] float4
 static size_t bwd_smem_bytes(int keys, int lmax) {
-  return (size_t)kBwdWarps * keys * 2 + (size_t)keys * 4 * 2 + 64 * 4 + (((size_t)lmax * 2 + 15) & ~(size_t)15);
+  return (size_t)kBwdWarps * keys * 2 + (size_t)keys * 4 * 2 + 64 * 4 + (((size_t)lmax * 2 + 15) & ~(size_t)15) +
+         (lmax <= kBwdStageMax ? (size_t)lmax * 16 : 0);
 }
 
-template <int K>
+template <int K, bool STAGE>
 __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
   constexpr int W = kBwdWarps;
   static_assert(K % kBwdThreads == 0, "whole keys per thread");
@@ -70,6 +76,31 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
   const float* oth_gd = (side ? a.gd1 : a.gd2) + (size_t)batch * L;
   const int* oth_idx = (side ? a.idx1 : a.idx2) + (size_t)batch * L;
   float* out = (side ? a.gxyz2 : a.gxyz1) + (size_t)batch * P * 3;
+
+  // partner cloud in shared memory (behind order[], whose length depends on max(n, m))
+  float4* pcloud = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(order) +
+                                           ((((size_t)(a.n > a.m ? a.n : a.m)) * 2 + 15) & ~(size_t)15));
+  if (STAGE) {
+    // issued first: the loads fly while the count tables are zeroed; the first __syncthreads
+    // below orders the stores before every use
+    for (int e0 = tid; e0 < L; e0 += 4 * kBwdThreads) {
+      float px[4], py[4], pz[4], pg[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * kBwdThreads;
+        const int es = e < L ? e : 0;
+        px[u] = __ldg(oth + (size_t)es * 3);
+        py[u] = __ldg(oth + (size_t)es * 3 + 1);
+        pz[u] = __ldg(oth + (size_t)es * 3 + 2);
+        pg[u] = __ldg(oth_gd + es);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * kBwdThreads;
+        if (e < L) pcloud[e] = make_float4(px[u], py[u], pz[u], pg[u]);
+      }
+    }
+  }
 
   const int seg = ((L + W - 1) / W + 31) & ~31;  // elements per warp, multiple of 32
   const int e_begin = warp * seg;
@@ -206,9 +237,18 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
         dx[i] = dy[i] = dz[i] = 0.f;
         if (ok[i] && j2[i] >= 0 && j2[i] < L) {
           const float g = __fmul_rn(gown[i], 2.0f);
-          dx[i] = __fmul_rn(g, __fsub_rn(ox[i], __ldg(oth + (size_t)j2[i] * 3)));
-          dy[i] = __fmul_rn(g, __fsub_rn(oy[i], __ldg(oth + (size_t)j2[i] * 3 + 1)));
-          dz[i] = __fmul_rn(g, __fsub_rn(oz[i], __ldg(oth + (size_t)j2[i] * 3 + 2)));
+          float tx, ty, tz;
+          if (STAGE) {
+            const float4 t4 = pcloud[j2[i]];
+            tx = t4.x; ty = t4.y; tz = t4.z;
+          } else {
+            tx = __ldg(oth + (size_t)j2[i] * 3);
+            ty = __ldg(oth + (size_t)j2[i] * 3 + 1);
+            tz = __ldg(oth + (size_t)j2[i] * 3 + 2);
+          }
+          dx[i] = __fmul_rn(g, __fsub_rn(ox[i], tx));
+          dy[i] = __fmul_rn(g, __fsub_rn(oy[i], ty));
+          dz[i] = __fmul_rn(g, __fsub_rn(oz[i], tz));
         }
         ax[i] = ay[i] = az[i] = 0.f;
         if (side == 0) {  // loop 1 (direct) runs before loop 2 (scatter) for cloud 1
@@ -223,10 +263,20 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
         for (int i = 0; i < PER; i++) {
           if (r < cn[i]) {
             const int e = order[s0[i] + r];
-            const float g = __fmul_rn(__ldg(oth_gd + e), 2.0f);
-            const float tx = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3), ox[i]));
-            const float ty = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 1), oy[i]));
-            const float tz = __fmul_rn(g, __fsub_rn(__ldg(oth + (size_t)e * 3 + 2), oz[i]));
+            float ex, ey, ez, eg;
+            if (STAGE) {
+              const float4 t4 = pcloud[e];
+              ex = t4.x; ey = t4.y; ez = t4.z; eg = t4.w;
+            } else {
+              ex = __ldg(oth + (size_t)e * 3);
+              ey = __ldg(oth + (size_t)e * 3 + 1);
+              ez = __ldg(oth + (size_t)e * 3 + 2);
+              eg = __ldg(oth_gd + e);
+            }
+            const float g = __fmul_rn(eg, 2.0f);
+            const float tx = __fmul_rn(g, __fsub_rn(ex, ox[i]));
+            const float ty = __fmul_rn(g, __fsub_rn(ey, oy[i]));
+            const float tz = __fmul_rn(g, __fsub_rn(ez, oz[i]));
             ax[i] = __fsub_rn(ax[i], tx);
             ay[i] = __fsub_rn(ay[i], ty);
             az[i] = __fsub_rn(az[i], tz);
@@ -251,6 +301,196 @@ __global__ void __launch_bounds__(kBwdThreads) nn_bwd_kernel(const BwdArgs a) {
   }
 }
 
+
+// ---- second formulation (default for partner clouds up to kBwdStageMax points) ------------------
+// The stable counting sort above pays ~40 % of its time in match.any and keeps 16 count tables
+// (64 KB) per CTA.  Contributor lists are short (one entry on average), so here the inverse map is
+// built with plain shared-memory atomics in ARBITRARY order and the owner of an output point sorts
+// its own list (insertion sort, a handful of u16 in shared memory) before it walks it: the
+// summation order is again ascending source index, bit-identical to NnDistanceGradOp.  A point with
+// more than kBwd2Sort contributors (collapsed clouds) is served by a sequential scan of the staged
+// index array, which is ascending by construction.  Everything the walk touches (partner xyz,
+// grad_dist, indices) is staged once in shared memory; ~60 KB per CTA of 256 threads, so several
+// CTAs share an SM and hide each other's phase latencies.
+constexpr int kBwd2Threads = 256;
+constexpr int kBwd2Sort = 16;
+
+// smem: cnt[K] i32 | start[K + 32] i32 | wsum[32] i32 | keys[L] i32 | pcloud[L] float4 | order[L] u16
+static size_t bwd2_smem_bytes(int keys, int l_other_max) {
+  return (size_t)keys * 4 + (size_t)(keys + 32) * 4 + 32 * 4 + (size_t)l_other_max * 4 + (size_t)l_other_max * 16 +
+         (((size_t)l_other_max * 2 + 15) & ~(size_t)15);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) {
+  constexpr int T = kBwd2Threads, PER = K / T;
+  static_assert(K % T == 0, "whole keys per thread");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lmax = ((a.n > a.m ? a.n : a.m) + 3) & ~3;         // as the launcher: keeps pcloud 16-byte aligned
+  int* cnt = reinterpret_cast<int*>(smem_raw);                 // [K] counts, then fill counters
+  int* start = cnt + K;                                        // [K + 1] exclusive prefix
+  int* wsum = start + K + 32;                                  // [32]
+  int* keys = wsum + 32;                                       // [lmax] partner indices
+  float4* pcloud = reinterpret_cast<float4*>(keys + lmax);     // [lmax] {x, y, z, grad_dist}
+  unsigned short* order = reinterpret_cast<unsigned short*>(pcloud + lmax);  // [lmax]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int part = blockIdx.x % a.nparts;
+  const int batch = (blockIdx.x / a.nparts) >> 1;
+  const int side = (blockIdx.x / a.nparts) & 1;
+  const int P = side ? a.m : a.n;
+  const int L = side ? a.n : a.m;
+  const float* own = (side ? a.xyz2 : a.xyz1) + (size_t)batch * P * 3;
+  const float* oth = (side ? a.xyz1 : a.xyz2) + (size_t)batch * L * 3;
+  const float* own_gd = (side ? a.gd2 : a.gd1) + (size_t)batch * P;
+  const int* own_idx = (side ? a.idx2 : a.idx1) + (size_t)batch * P;
+  const float* oth_gd = (side ? a.gd1 : a.gd2) + (size_t)batch * L;
+  const int* oth_idx = (side ? a.idx1 : a.idx2) + (size_t)batch * L;
+  float* out = (side ? a.gxyz2 : a.gxyz1) + (size_t)batch * P * 3;
+
+  // stage the partner cloud once: indices, coordinates, upstream gradient (4 points per thread in flight)
+  for (int e0 = tid; e0 < L; e0 += 4 * T) {
+    float px[4], py[4], pz[4], pg[4];
+    int pk[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * T;
+      const int es = e < L ? e : 0;
+      px[u] = __ldg(oth + (size_t)es * 3);
+      py[u] = __ldg(oth + (size_t)es * 3 + 1);
+      pz[u] = __ldg(oth + (size_t)es * 3 + 2);
+      pg[u] = __ldg(oth_gd + es);
+      pk[u] = __ldg(oth_idx + es);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * T;
+      if (e < L) {
+        pcloud[e] = make_float4(px[u], py[u], pz[u], pg[u]);
+        keys[e] = pk[u];
+      }
+    }
+  }
+
+  for (int k0 = part * K; k0 < P; k0 += a.nparts * K) {
+    const int kn = min(K, P - k0);
+    for (int i = tid; i < K; i += T) cnt[i] = 0;
+    __syncthreads();
+    // 1. contributors per output point
+    for (int e = tid; e < L; e += T) {
+      const int kk = keys[e] - k0;
+      if (kk >= 0 && kk < kn) atomicAdd(&cnt[kk], 1);
+    }
+    __syncthreads();
+    // 2. exclusive prefix over the keys (PER consecutive keys per thread); counts become fill counters
+    {
+      int loc[PER];
+      int s = 0;
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        loc[i] = s;
+        s += cnt[tid * PER + i];
+      }
+      int incl = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      int woff = 0;
+      for (int w = 0; w < warp; w++) woff += wsum[w];
+      const int base = woff + incl - s;
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        start[tid * PER + i] = base + loc[i];
+        cnt[tid * PER + i] = 0;
+      }
+      if (tid == T - 1) start[K] = base + s;
+    }
+    __syncthreads();
+    // 3. placement, arbitrary order inside a list
+    for (int e = tid; e < L; e += T) {
+      const int kk = keys[e] - k0;
+      if (kk >= 0 && kk < kn) order[start[kk] + atomicAdd(&cnt[kk], 1)] = (unsigned short)e;
+    }
+    __syncthreads();
+    // 4. one thread per output point: sort its list, walk it in ascending order
+    {
+      float ox[PER], oy[PER], oz[PER], gown[PER];
+      int j2[PER];
+      bool ok[PER];
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        const int k = tid + i * T;
+        ok[i] = k < kn;
+        const int p = k0 + (ok[i] ? k : 0);
+        ox[i] = __ldg(own + (size_t)p * 3);
+        oy[i] = __ldg(own + (size_t)p * 3 + 1);
+        oz[i] = __ldg(own + (size_t)p * 3 + 2);
+        j2[i] = __ldg(own_idx + p);
+        gown[i] = __ldg(own_gd + p);
+      }
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        if (!ok[i]) continue;
+        const int k = tid + i * T;
+        const int s0 = start[k], cn = start[k + 1] - s0;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (j2[i] >= 0 && j2[i] < L) {  // direct term (own loop of the reference)
+          const float4 t4 = pcloud[j2[i]];
+          const float g = __fmul_rn(gown[i], 2.0f);
+          dx = __fmul_rn(g, __fsub_rn(ox[i], t4.x));
+          dy = __fmul_rn(g, __fsub_rn(oy[i], t4.y));
+          dz = __fmul_rn(g, __fsub_rn(oz[i], t4.z));
+        }
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        if (side == 0) {  // loop 1 (direct) runs before loop 2 (scatter) for cloud 1
+          ax = __fadd_rn(ax, dx);
+          ay = __fadd_rn(ay, dy);
+          az = __fadd_rn(az, dz);
+        }
+        auto sub = [&](int e) {
+          const float4 t4 = pcloud[e];
+          const float g = __fmul_rn(t4.w, 2.0f);
+          ax = __fsub_rn(ax, __fmul_rn(g, __fsub_rn(t4.x, ox[i])));
+          ay = __fsub_rn(ay, __fmul_rn(g, __fsub_rn(t4.y, oy[i])));
+          az = __fsub_rn(az, __fmul_rn(g, __fsub_rn(t4.z, oz[i])));
+        };
+        if (cn <= kBwd2Sort) {
+          for (int r = 1; r < cn; r++) {  // insertion sort of a short list
+            const unsigned short v = order[s0 + r];
+            int q = r - 1;
+            while (q >= 0 && order[s0 + q] > v) {
+              order[s0 + q + 1] = order[s0 + q];
+              q--;
+            }
+            order[s0 + q + 1] = v;
+          }
+          for (int r = 0; r < cn; r++) sub(order[s0 + r]);
+        } else {
+          const int want = k0 + k;
+          for (int e = 0; e < L; e++)
+            if (keys[e] == want) sub(e);
+        }
+        if (side == 1) {  // for cloud 2 the scatter of loop 1 comes first, its own loop 2 last
+          ax = __fadd_rn(ax, dx);
+          ay = __fadd_rn(ay, dy);
+          az = __fadd_rn(az, dz);
+        }
+        const int p = k0 + k;
+        out[(size_t)p * 3] = ax;
+        out[(size_t)p * 3 + 1] = ay;
+        out[(size_t)p * 3 + 2] = az;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int g_bwd_kernel = 0;  // tuning hook (key 14): 0 auto (second formulation when it applies), 1 = stable counting sort
+int g_bwd_stage = 1;   // tuning hook (key 13): 0 = gather the partner cloud from global memory (no staging)
 int g_bwd_split = -1;  // tuning hook (key 9): -1 auto, 0 one CTA per cloud, 1 output points split over 4 CTAs
 
 }  // namespace ga
@@ -289,6 +529,39 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
   // Up to one wave of split CTAs: split the output points (measured, 2048-point clouds: B=1 17.4 ->
   // 14.3 us, B=10 18.4 -> 14.3 us); more cloud pairs: one CTA per cloud walks the contributors only
   // once (B=50 18.4 vs 27.5 us split, B=512 82 vs 184 us).
+  if (g_bwd_kernel != 1 && lmax <= kBwdStageMax) {
+    // CTAs per (batch element, cloud): enough to give every SM about two CTAs, each part at least 512 keys
+    int parts = 1;
+    if (g_bwd_split >= 0) {
+      parts = g_bwd_split == 0 ? 1 : (g_bwd_split == 1 ? 4 : g_bwd_split);
+    } else {
+      while (parts < 4 && (long long)2 * b * parts < 2LL * sm_count() && (lmax + parts * 2 - 1) / (parts * 2) >= 512) parts *= 2;
+    }
+    const int per = (lmax + parts - 1) / parts;
+    a.nparts = parts;
+    static std::atomic<unsigned> done2{0};
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done2.load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd2_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bwd2_smem_bytes(2048, kBwdStageMax)));
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bwd2_smem_bytes(1024, kBwdStageMax)));
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bwd2_smem_bytes(512, kBwdStageMax)));
+      done2.fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
+    const unsigned grid = (unsigned)(2 * b * parts);
+    const int lpad = (lmax + 3) & ~3;  // keeps the float4 array behind the int array 16-byte aligned
+    if (per <= 512)
+      nn_bwd2_kernel<512><<<grid, kBwd2Threads, bwd2_smem_bytes(512, lpad), st>>>(a);
+    else if (per <= 1024)
+      nn_bwd2_kernel<1024><<<grid, kBwd2Threads, bwd2_smem_bytes(1024, lpad), st>>>(a);
+    else
+      nn_bwd2_kernel<2048><<<grid, kBwd2Threads, bwd2_smem_bytes(2048, lpad), st>>>(a);
+    GA_LAUNCH_CHECK("nn_bwd2_kernel");
+    return GA_OK;
+  }
   int split = g_bwd_split;
   if (split < 0) split = (long long)b * 8 <= (long long)sm_count() ? 1 : 0;
   {
@@ -297,19 +570,27 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
     int dev = 0;
     GA_CUDA_TRY(cudaGetDevice(&dev));
     if (!(done_mask.load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
-      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)bwd_smem_bytes(2048, 65536)));
-      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)bwd_smem_bytes(512, 65536)));
+      // the largest requests: staged partner at kBwdStageMax points; unstaged at 65536 points
+      const size_t big2048 = bwd_smem_bytes(2048, 65536) > bwd_smem_bytes(2048, kBwdStageMax)
+                                 ? bwd_smem_bytes(2048, 65536) : bwd_smem_bytes(2048, kBwdStageMax);
+      const size_t big512 = bwd_smem_bytes(512, 65536) > bwd_smem_bytes(512, kBwdStageMax)
+                                ? bwd_smem_bytes(512, 65536) : bwd_smem_bytes(512, kBwdStageMax);
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<2048, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big2048));
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<2048, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big2048));
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big512));
+      GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big512));
       done_mask.fetch_or(1u << (dev & 31), std::memory_order_relaxed);
     }
   }
+  const bool stage = lmax <= kBwdStageMax && g_bwd_stage != 0;
   if (split) {
     a.nparts = (lmax + 511) / 512 < 4 ? (lmax + 511) / 512 : 4;
-    nn_bwd_kernel<512><<<(unsigned)(2 * b * a.nparts), kBwdThreads, bwd_smem_bytes(512, lmax), st>>>(a);
+    auto k = stage ? nn_bwd_kernel<512, true> : nn_bwd_kernel<512, false>;
+    k<<<(unsigned)(2 * b * a.nparts), kBwdThreads, bwd_smem_bytes(512, lmax), st>>>(a);
   } else {
     a.nparts = 1;
-    nn_bwd_kernel<2048><<<(unsigned)(2 * b), kBwdThreads, bwd_smem_bytes(2048, lmax), st>>>(a);
+    auto k = stage ? nn_bwd_kernel<2048, true> : nn_bwd_kernel<2048, false>;
+    k<<<(unsigned)(2 * b), kBwdThreads, bwd_smem_bytes(2048, lmax), st>>>(a);
   }
   GA_LAUNCH_CHECK("nn_bwd_kernel");
   return GA_OK;

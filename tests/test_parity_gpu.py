@@ -311,16 +311,22 @@ def check_bwd(ga, oracle, a, b, gd1, i1, gd2, i2):
     from geometric_adv_b200 import _lib
     lib = _lib.load()
     w1, w2 = oracle.nn_distance_grad(a, b, gd1, i1, gd2, i2)
-    for split in (0, 1, -1):
+    # kernel 0: shared-memory atomics + per-list sort (1, 2, 4 CTAs per cloud, auto); kernel 1: stable
+    # counting sort (one CTA per cloud / 4 CTAs, partner cloud staged in shared memory or gathered)
+    combos = [(0, 0, 1), (0, 2, 1), (0, 1, 1), (0, -1, 1), (1, 0, 1), (1, 1, 1), (1, 0, 0), (1, 1, 0)]
+    for kernel, split, stage in combos:
+        lib.ga_set_tuning(14, kernel)
         lib.ga_set_tuning(9, split)
+        lib.ga_set_tuning(13, stage)
         try:
             g1, g2 = ga.nn_distance_grad(t(a), t(b), t(gd1), t(i1), t(gd2), t(i2))
         finally:
+            lib.ga_set_tuning(14, 0)
             lib.ga_set_tuning(9, -1)
-        assert bits_equal(g1.cpu().numpy(), w1), "grad_xyz1 (split %d): %d mismatches" % (
-            split, int(np.sum(g1.cpu().numpy() != w1)))
-        assert bits_equal(g2.cpu().numpy(), w2), "grad_xyz2 (split %d): %d mismatches" % (
-            split, int(np.sum(g2.cpu().numpy() != w2)))
+            lib.ga_set_tuning(13, 1)
+        tag = "kernel %d, split %d, stage %d" % (kernel, split, stage)
+        assert bits_equal(g1.cpu().numpy(), w1), "grad_xyz1 (%s): %d mismatches" % (tag, int(np.sum(g1.cpu().numpy() != w1)))
+        assert bits_equal(g2.cpu().numpy(), w2), "grad_xyz2 (%s): %d mismatches" % (tag, int(np.sum(g2.cpu().numpy() != w2)))
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 5, 9), (3, 100, 200), (2, 2048, 2048), (1, 2500, 2048),

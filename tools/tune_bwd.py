@@ -30,8 +30,10 @@ for b in (1, 10, 50, 150, 512):
         lib.ga_nn_distance_bwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(g1.data_ptr()), p(i1.data_ptr()),
                                p(g1.data_ptr()), p(i2.data_ptr()), p(o1.data_ptr()), p(o2.data_ptr()), p(st))
 
-    for split in (0, 1):
+    for kernel, split, stage in ((0, 0, 1), (0, 2, 1), (0, 1, 1), (0, -1, 1), (1, 0, 1), (1, 1, 1)):
+        lib.ga_set_tuning(14, kernel)
         lib.ga_set_tuning(9, split)
+        lib.ga_set_tuning(13, stage)
         for _ in range(5):
             call()
         ts = []
@@ -42,5 +44,7 @@ for b in (1, 10, 50, 150, 512):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
-        print("bwd B=%d split=%d min %.2f us med %.2f us" % (b, split, ts[0] * 1e3, ts[len(ts) // 2] * 1e3), flush=True)
+        print("bwd B=%d kernel=%d split=%d stage=%d min %.2f us med %.2f us" % (b, kernel, split, stage, ts[0] * 1e3, ts[len(ts) // 2] * 1e3), flush=True)
     lib.ga_set_tuning(9, -1)
+    lib.ga_set_tuning(13, 1)
+    lib.ga_set_tuning(14, 0)
