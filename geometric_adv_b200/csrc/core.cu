@@ -25,6 +25,7 @@ extern int g_host_graph_epoch;   // host_api.cu
 extern int g_umma_grid;          // nn_distance_fwd_umma.cu
 extern int g_bwd_stage;          // nn_distance_bwd.cu
 extern int g_bwd_kernel;         // nn_distance_bwd.cu
+extern int g_pdl;                // nn_distance_bwd.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -138,6 +139,10 @@ int ga_set_tuning(int key, int value) {
   if (key == 10) {
     ga::g_host_graph = value;
     ga::g_host_graph_epoch++;
+    return GA_OK;
+  }
+  if (key == 15) {
+    ga::g_pdl = value;
     return GA_OK;
   }
   if (key == 14) {

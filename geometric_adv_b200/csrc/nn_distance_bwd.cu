@@ -348,10 +348,12 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
   const int* oth_idx = (side ? a.idx1 : a.idx2) + (size_t)batch * L;
   float* out = (side ? a.gxyz2 : a.gxyz1) + (size_t)batch * P * 3;
 
-  // stage the partner cloud once: indices, coordinates, upstream gradient (4 points per thread in flight)
+  // Stage the partner cloud once (4 points per thread in flight).  The coordinates are inputs of the
+  // forward kernel too, so they may be read while that kernel is still finishing (programmatic
+  // dependent launch: this grid starts early and waits here); indices and upstream gradients come
+  // from the preceding kernels and are read after the wait.
   for (int e0 = tid; e0 < L; e0 += 4 * T) {
-    float px[4], py[4], pz[4], pg[4];
-    int pk[4];
+    float px[4], py[4], pz[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int e = e0 + u * T;
@@ -359,14 +361,29 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
       px[u] = __ldg(oth + (size_t)es * 3);
       py[u] = __ldg(oth + (size_t)es * 3 + 1);
       pz[u] = __ldg(oth + (size_t)es * 3 + 2);
-      pg[u] = __ldg(oth_gd + es);
-      pk[u] = __ldg(oth_idx + es);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * T;
+      if (e < L) pcloud[e] = make_float4(px[u], py[u], pz[u], 0.0f);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int e0 = tid; e0 < L; e0 += 4 * T) {
+    float pg[4];
+    int pk[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * T;
+      const int es = e < L ? e : 0;
+      pg[u] = oth_gd[es];   // plain loads: written by the kernel this grid depends on
+      pk[u] = oth_idx[es];
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int e = e0 + u * T;
       if (e < L) {
-        pcloud[e] = make_float4(px[u], py[u], pz[u], pg[u]);
+        reinterpret_cast<float*>(pcloud + e)[3] = pg[u];   // same thread wrote x, y, z
         keys[e] = pk[u];
       }
     }
@@ -429,8 +446,8 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
         ox[i] = __ldg(own + (size_t)p * 3);
         oy[i] = __ldg(own + (size_t)p * 3 + 1);
         oz[i] = __ldg(own + (size_t)p * 3 + 2);
-        j2[i] = __ldg(own_idx + p);
-        gown[i] = __ldg(own_gd + p);
+        j2[i] = own_idx[p];
+        gown[i] = own_gd[p];
       }
 #pragma unroll
       for (int i = 0; i < PER; i++) {
@@ -489,6 +506,7 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
   }
 }
 
+int g_pdl = 1;         // tuning hook (key 15): 0 = plain launches (no programmatic dependent launch)
 int g_bwd_kernel = 0;  // tuning hook (key 14): 0 auto (second formulation when it applies), 1 = stable counting sort
 int g_bwd_stage = 1;   // tuning hook (key 13): 0 = gather the partner cloud from global memory (no staging)
 int g_bwd_split = -1;  // tuning hook (key 9): -1 auto, 0 one CTA per cloud, 1 output points split over 4 CTAs
@@ -553,12 +571,28 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
     }
     const unsigned grid = (unsigned)(2 * b * parts);
     const int lpad = (lmax + 3) & ~3;  // keeps the float4 array behind the int array 16-byte aligned
-    if (per <= 512)
-      nn_bwd2_kernel<512><<<grid, kBwd2Threads, bwd2_smem_bytes(512, lpad), st>>>(a);
-    else if (per <= 1024)
-      nn_bwd2_kernel<1024><<<grid, kBwd2Threads, bwd2_smem_bytes(1024, lpad), st>>>(a);
-    else
-      nn_bwd2_kernel<2048><<<grid, kBwd2Threads, bwd2_smem_bytes(2048, lpad), st>>>(a);
+    // Programmatic dependent launch: the grid may start while the preceding kernel of the stream (the
+    // forward search, which triggers early) drains, and blocks in griddepcontrol.wait before it reads
+    // anything that kernel wrote.  After a kernel that never triggers this is an ordinary launch.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kBwd2Threads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    if (per <= 512) {
+      cfg.dynamicSmemBytes = bwd2_smem_bytes(512, lpad);
+      GA_CUDA_TRY(cudaLaunchKernelEx(&cfg, nn_bwd2_kernel<512>, a));
+    } else if (per <= 1024) {
+      cfg.dynamicSmemBytes = bwd2_smem_bytes(1024, lpad);
+      GA_CUDA_TRY(cudaLaunchKernelEx(&cfg, nn_bwd2_kernel<1024>, a));
+    } else {
+      cfg.dynamicSmemBytes = bwd2_smem_bytes(2048, lpad);
+      GA_CUDA_TRY(cudaLaunchKernelEx(&cfg, nn_bwd2_kernel<2048>, a));
+    }
     GA_LAUNCH_CHECK("nn_bwd2_kernel");
     return GA_OK;
   }

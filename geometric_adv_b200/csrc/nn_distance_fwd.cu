@@ -35,6 +35,8 @@ namespace ga {
 template <class Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_kernel(const FwdArgs a) {
   constexpr int THREADS = Cfg::kThreads, Q = Cfg::kQ, QT = Cfg::kQT, T = Cfg::kT, CH = Cfg::kCH;
+  // dependents (the gradient kernel) may be scheduled once every CTA of this grid has started
+  asm volatile("griddepcontrol.launch_dependents;");
   extern __shared__ float4 smem_f4[];
   float4* tgt = smem_f4;                                             // [CH/2 (+pad)][2]
   float* red = reinterpret_cast<float*>(smem_f4 + CH + 2 * kPipeU);  // [32]

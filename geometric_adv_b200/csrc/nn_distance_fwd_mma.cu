@@ -138,6 +138,8 @@ __device__ __forceinline__ void mma_write(const QueryState<2>& s, int qbase, int
 template <class Cfg, int MODE, int MINB>
 __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const FwdArgs a) {
   constexpr int THREADS = Cfg::kThreads, QT = Cfg::kQT, CH = Cfg::kCH, T = kMmaT;
+  // dependents (the gradient kernel) may be scheduled once every CTA of this grid has started
+  asm volatile("griddepcontrol.launch_dependents;");
   extern __shared__ float4 smem_f4[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
   float4* tgt = smem_f4;
