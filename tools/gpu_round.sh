@@ -21,6 +21,11 @@ for what in fwd bwd knn; do
 done
 GA_TUNE=0=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:nn_fwd -s 2 -c 1 -f \
   -o gpurun_out/${TAG}_fwdfp32 python tools/prof.py fwd 50 > gpurun_out/ncu_fwdfp32.log 2>&1
+GA_TUNE=0=22 timeout 300 ncu --set full --clock-control none --import-source on -k regex:nn_fwd -s 2 -c 1 -f \
+  -o gpurun_out/${TAG}_fwdumma python tools/prof.py fwd 50 > gpurun_out/ncu_fwdumma.log 2>&1
+timeout 120 python tools/umma_trace.py 50 > gpurun_out/umma_trace.txt 2>&1
+timeout 200 python tools/tune_bwd.py > gpurun_out/tune_bwd.log 2>&1
+timeout 300 python tools/tune_e2e.py > gpurun_out/tune_e2e.log 2>&1
 timeout 300 python tools/tune_mma.py > gpurun_out/tune_mma.log 2>&1
 timeout 120 tools/mmabench.bin > gpurun_out/mmabench.txt 2>&1
 timeout 120 tools/tmembench.bin > gpurun_out/tmembench.txt 2>&1

@@ -17,13 +17,16 @@ for rep in sorted(os.listdir(G)):
             d = dict(zip(h, v))
             kn = d.get("Kernel Name", "").split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
             if kn.startswith("nn_fwd") and "_fwd" in rep:
+                units = dict(zip(h, rows[1]))
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
                 def mb(x):
-                    return float(d[x]) * 1e6 if d.get(x) else 0.0
+                    return float(d[x]) * scale.get(units.get(x, "byte"), 1.0) if d.get(x) else 0.0
                 tp = os.path.join(P, "traffic.json")
                 tr = json.load(open(tp)) if os.path.exists(tp) else {}
                 tr[kn + "_b50_dram_bytes_per_launch"] = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
                 tr[kn + "_source"] = rep
-                tr["note"] = "dram__bytes_read.sum + dram__bytes_write.sum (Mbyte units in the report)"
+                tr["note"] = "dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch"
                 json.dump(tr, open(tp, "w"), indent=1)
 for name in ("tune.json", "microbench.txt", "loopbench.txt", "bench_%s.json" % tag):
     src = os.path.join(G, name)

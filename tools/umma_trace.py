@@ -45,15 +45,15 @@ iss = t[0]
 n = int((iss[:, 1] != 0).sum())
 print("issuer: %d steps" % n)
 for s in list(range(0, min(n, 40))):
-    d0 = t[1 + (s & 1)][s >> 1]
-    print("  step %3d: empty-wait done %7d  issued %7d (+%d) | drain grp %d: full-wait start %7d done %7d (waited %d, issue->visible %d)" % (
+    d0 = t[1][s]
+    print("  step %3d: empty-wait done %7d  issued %7d (+%d) | drain warp 0 (%d): full-wait start %7d done %7d (waited %d, issue->visible %d)" % (
         s, iss[s, 0] - t0, iss[s, 1] - t0, iss[s, 1] - iss[s, 0], s & 1, d0[0] - t0 if d0[0] else -1,
         d0[1] - t0 if d0[1] else -1, d0[1] - d0[0], d0[1] - iss[s, 1] if d0[1] else -1))
 gaps = np.diff(iss[:n, 1])
 print("issue-to-issue gap: median %.0f mean %.0f max %d cycles" % (np.median(gaps), gaps.mean(), gaps.max()))
 w = []
 for s in range(4, n):
-    d0 = t[1 + (s & 1)][s >> 1]
+    d0 = t[1][s]
     if d0[0] and d0[1]:
         w.append((d0[1] - d0[0], d0[1] - iss[s, 1]))
 w = np.array(w)
