@@ -182,26 +182,54 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
 
 // ---- persistent variant: one CTA of 16 warps per SM, warps pull 64-query jobs ----------------
 // The scan is bound by the HMMA pipe (0.5 HMMA.16816 per clock and SM); staging, list building and
-// refine are not.  With one job per warp and a barrier per CTA the phases of the resident warps
-// line up and the tensor pipe idles while they stage or refine; with few CTAs per SM (B=50: 2.7)
-// the last wave is short of work.  Here every SM gets an equal, contiguous share of all
-// (batch, direction, 64-query) jobs.  A share is cut into segments of one target cloud each; the
-// 16 warps stage the cloud once (one 128-target block per warp, no CTA barrier inside), then pull
-// jobs from a shared counter and run scan / refine / write on their own, so that their phases
-// drift apart.  A warp that finds the segment drained stages its block of the NEXT segment into
-// the other buffer before the one barrier per segment.  Clouds of at most 2048 points.
+// refine are not.  The grid of nn_fwd_mma_kernel quantises the work in CTAs of 512 queries: at B=50
+// 400 CTAs on 296 slots leave a 23 % tail (sm__cycles_active.avg 84 K vs elapsed 109 K).  Here every
+// SM gets an equal, contiguous share of all (batch, direction, 64-query) warp jobs (B=50: 21.6 jobs
+// for 16 warps).  A share is walked in super-steps of up to TWO target clouds: both are staged (one
+// 128-target block per warp and cloud: pair-SoA + B fragments, 96 KB each), one barrier, then the 16
+// warps pull jobs of both clouds from a shared counter and run scan / refine / write on their own,
+// so their phases drift apart and nobody waits at a cloud boundary; one barrier closes the
+// super-step.  At B=50 a share crosses at most one cloud boundary: two barriers per kernel.
+// Clouds of at most 2048 points.
 constexpr int kPersistWarps = 16;
 constexpr int kPersistCH = 2048;
 constexpr size_t kPersistBuf = (size_t)kPersistCH * 16 + (size_t)kPipeU * 32 + (size_t)kPersistCH * 32;
 constexpr size_t kPersistOffRed = 2 * kPersistBuf;                         // [2][16] float
-constexpr size_t kPersistOffCtr = kPersistOffRed + 2 * 16 * 4;             // [2] int (+pad)
-constexpr size_t kPersistOffCnt = kPersistOffCtr + 16;                     // [16][64] int
+constexpr size_t kPersistOffCtr = kPersistOffRed + 2 * 16 * 4;             // job counter, control block, cursor
+constexpr size_t kPersistOffCnt = kPersistOffCtr + 80;                     // [16][64] int
 constexpr size_t kPersistOffTile = kPersistOffCnt + kPersistWarps * kMmaQW * 4;  // [16][64][2] u16
 constexpr size_t kPersistSmem = kPersistOffTile + kPersistWarps * kMmaQW * 4;
+
+// One 64-query job of the persistent kernel.  Deliberately NOT inlined: inside the kernel's nested
+// loops ptxas serialises the four HMMAs of a scan step on one accumulator quad (a NOP after every
+// HMMA, 25 % slower scan); as a function of its own the scan gets the same schedule as in
+// nn_fwd_mma_kernel (three rotating accumulator quads).
+template <int MODE>
+__device__ __noinline__ void persist_job(const FwdArgs& a, int batch, bool rev, int qbase, const unsigned char* bufp,
+                                         float bm, int* wcnt, unsigned short* wtile) {
+  const int lane = threadIdx.x & 31;
+  const int nq = rev ? a.m : a.n;
+  const int nt = rev ? a.n : a.m;
+  const float* qpts = (rev ? a.xyz2 : a.xyz1) + (size_t)batch * nq * 3;
+  const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
+  const float4* tgt = reinterpret_cast<const float4*>(bufp);
+  const uint4* bfrag = reinterpret_cast<const uint4*>(bufp + (size_t)kPersistCH * 16 + (size_t)kPipeU * 32);
+  MmaRows R;
+  mma_load_rows(R, qpts, nq, qbase, lane);
+  QueryState<2> s;
+  mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane);
+  float mrun[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
+  mma_chunk<MODE>(R, s, mrun, tgt, bfrag, 0, nt, nt, bm, wcnt, wtile, lane);
+  mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
+            rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kPersistWarps * 32, 1)
     nn_fwd_mma_persist_kernel(const FwdArgs a, const int wt1, const int wt2, const long long J) {
+  asm volatile("griddepcontrol.launch_dependents;");
   extern __shared__ float4 smem_f4[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
   float* red = reinterpret_cast<float*>(smem + kPersistOffRed);
@@ -210,19 +238,14 @@ __global__ void __launch_bounds__(kPersistWarps * 32, 1)
   int* wcnt = reinterpret_cast<int*>(smem + kPersistOffCnt) + warp * kMmaQW;
   unsigned short* wtile = reinterpret_cast<unsigned short*>(smem + kPersistOffTile) + warp * kMmaQW * 2;
 
-  const long long jpb = (long long)wt1 + wt2;
-  const long long j0 = J * blockIdx.x / gridDim.x, j1 = J * (blockIdx.x + 1) / gridDim.x;
+  // Control block of a super-step, written by thread 0 and read back from shared memory inside the job
+  // loop: the 64-bit job arithmetic must not stay live across the scan (with it in registers ptxas
+  // serialises the four HMMAs of a step on ONE accumulator quad and the scan runs 25 % slower).
+  //   ctl[4 s + 0..3] = batch, direction, first query, jobs of segment s (0 / 1); ctl[8] = done flag
+  volatile int* ctl = reinterpret_cast<volatile int*>(smem + kPersistOffCtr + 16);
+  long long* jcur = reinterpret_cast<long long*>(smem + kPersistOffCtr + 64);
 
-  // segment of job j: one (batch, direction); this CTA's part of it is [j, pend)
-  auto segment = [&](long long j, int& batch, bool& rev, long long& sbeg, long long& pend) {
-    batch = (int)(j / jpb);
-    const long long r = j - (long long)batch * jpb;
-    rev = r >= wt1;
-    sbeg = (long long)batch * jpb + (rev ? wt1 : 0);
-    const long long send = sbeg + (rev ? wt2 : wt1);
-    pend = send < j1 ? send : j1;
-  };
-  auto stage = [&](int buf, int batch, bool rev) {
+  auto stage = [&](int buf, int batch, bool rev) {  // this warp's 128-target block of a target cloud
     const int nt = rev ? a.n : a.m;
     const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
     float4* tgt = reinterpret_cast<float4*>(smem + buf * kPersistBuf);
@@ -233,64 +256,55 @@ __global__ void __launch_bounds__(kPersistWarps * 32, 1)
     if (lane == 0) red[buf * 16 + warp] = lmax;
   };
 
-  long long j = j0;
-  int k = 0;
-  if (j < j1) {
-    int batch;
-    bool rev;
-    long long sbeg, pend;
-    segment(j, batch, rev, sbeg, pend);
-    stage(0, batch, rev);
-    if (tid == 0) counter[0] = 0;
-  }
-  __syncthreads();
-  while (j < j1) {
-    const int buf = k & 1;
-    int batch;
-    bool rev;
-    long long sbeg, pend;
-    segment(j, batch, rev, sbeg, pend);
-    const int nq = rev ? a.m : a.n;
-    const int nt = rev ? a.n : a.m;
-    const float* qpts = (rev ? a.xyz2 : a.xyz1) + (size_t)batch * nq * 3;
-    const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
-    const float4* tgt = reinterpret_cast<const float4*>(smem + buf * kPersistBuf);
-    const uint4* bfrag =
-        reinterpret_cast<const uint4*>(smem + buf * kPersistBuf + (size_t)kPersistCH * 16 + (size_t)kPipeU * 32);
-    float bm = 0.0f;
-#pragma unroll
-    for (int w = 0; w < 16; w++) bm = fmaxf(bm, red[buf * 16 + w]);
-    if (tid == 0) counter[buf ^ 1] = (int)(pend - j0);  // first job of the next segment
-
-    for (;;) {
-      int jo = 0;
-      if (lane == 0) jo = atomicAdd(&counter[buf], 1);
-      jo = __shfl_sync(0xffffffffu, jo, 0);
-      const long long job = j0 + jo;
-      if (job >= pend) break;
-      const int qbase = (int)(job - sbeg) * kMmaQW;
-      MmaRows R;
-      mma_load_rows(R, qpts, nq, qbase, lane);
-      QueryState<2> s;
-      mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane);
-      float mrun[8];
-#pragma unroll
-      for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
-      mma_chunk<MODE>(R, s, mrun, tgt, bfrag, 0, nt, nt, bm, wcnt, wtile, lane);
-      mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq,
-                (rev ? a.idx2 : a.idx1) + (size_t)batch * nq, rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1,
-                (size_t)batch * nq);
-    }
-    if (pend < j1) {  // this warp's block of the next segment, into the other buffer
-      int nb;
-      bool nrev;
-      long long nsbeg, npend;
-      segment(pend, nb, nrev, nsbeg, npend);
-      stage(buf ^ 1, nb, nrev);
+  if (tid == 0) *jcur = J * blockIdx.x / gridDim.x;
+  for (;;) {
+    if (tid == 0) {
+      const long long jpb = (long long)wt1 + wt2;
+      const long long j1 = J * (blockIdx.x + 1) / gridDim.x;
+      long long j = *jcur;
+      ctl[8] = j >= j1;
+      for (int sgm = 0; sgm < 2; sgm++) {
+        int batch = 0, rev = 0, firstq = 0, njobs = 0;
+        if (j < j1) {
+          batch = (int)(j / jpb);
+          const long long r = j - (long long)batch * jpb;
+          rev = r >= wt1;
+          const long long sbeg = (long long)batch * jpb + (rev ? wt1 : 0);
+          const long long send = sbeg + (rev ? wt2 : wt1);
+          const long long pend = send < j1 ? send : j1;
+          firstq = (int)(j - sbeg) * kMmaQW;
+          njobs = (int)(pend - j);
+          j = pend;
+        }
+        ctl[4 * sgm] = batch;
+        ctl[4 * sgm + 1] = rev;
+        ctl[4 * sgm + 2] = firstq;
+        ctl[4 * sgm + 3] = njobs;
+      }
+      *jcur = j;
+      *counter = 0;
     }
     __syncthreads();
-    j = pend;
-    k++;
+    if (ctl[8]) break;
+    stage(0, ctl[0], ctl[1] != 0);
+    if (ctl[7] > 0) stage(1, ctl[4], ctl[5] != 0);
+    __syncthreads();
+    for (;;) {
+      int jo = 0;
+      if (lane == 0) jo = atomicAdd(counter, 1);
+      jo = __shfl_sync(0xffffffffu, jo, 0);
+      const int na = ctl[3];
+      if (jo >= na + ctl[7]) break;
+      const int sgm = jo >= na ? 1 : 0;
+      const int batch = ctl[4 * sgm];
+      const bool rev = ctl[4 * sgm + 1] != 0;
+      const int qbase = ctl[4 * sgm + 2] + (jo - (sgm ? na : 0)) * kMmaQW;
+      float bm = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 16; w++) bm = fmaxf(bm, red[sgm * 16 + w]);
+      persist_job<MODE>(a, batch, rev, qbase, smem + (sgm ? kPersistBuf : 0), bm, wcnt, wtile);
+    }
+    __syncthreads();  // both buffers, the counter and the control block are free again
   }
 }
 
