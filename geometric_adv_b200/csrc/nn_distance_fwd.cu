@@ -105,6 +105,9 @@ __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_split_kernel(const FwdAr
   const float kInf = __int_as_float(0x7f800000);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
+  // A CTA may write a peer's shared memory only once that peer has started executing: arrive now,
+  // wait right before the first remote store (the local scan in between hides the barrier).
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   extern __shared__ float4 smem_f4[];
   float4* tgt = smem_f4;
   float* red = reinterpret_cast<float*>(smem_f4 + CH + 2 * kPipeU);  // [32]
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) nn_fwd_split_kernel(const FwdAr
   TileTrack<Q> tr;
   search_phase1<Cfg>(s, tgt, ntl, tr);
 
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // every CTA of the cluster is running
   for (int rr = 0; rr < S; rr++) {  // publish this CTA's filter minima to every CTA of the cluster
     float* dst = cluster.map_shared_rank(xf, rr);
 #pragma unroll

@@ -34,8 +34,11 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // MODE 1: zero C, B from shared memory, 2 FMNMX3 per MMA (the real inner loop)
 // MODE 2: as 1 without the FMNMX3 (results folded with one add per MMA to keep them alive)
 // MODE 3: as 1 with B kept in registers (no LDS)
+// MODE 4: as 1 with the zero C operand in a REAL register quad (opaque to the compiler) instead of RZ
+// MODE 5: as 2 (no FMNMX3) with the real-register zero C
+// MODE 6: chained accumulators + LDS (c += a*b, B from shared memory)
 template <int MODE, int MT>
-__global__ void __launch_bounds__(512) bench(float* out, int steps, long long* cyc) {
+__global__ void __launch_bounds__(512) bench(float* out, int steps, long long* cyc, float rzero) {
   __shared__ uint2 bfrag[64 * 32];
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) bfrag[i] = make_uint2(0x3f803f80u + i, 0x3f803f80u);
@@ -47,7 +50,11 @@ __global__ void __launch_bounds__(512) bench(float* out, int steps, long long* c
     for (int r = 0; r < 4; r++) a[i][r] = 0x3f803f80u + lane + i * 7 + r;
   float c[MT][4];
   float rm[MT][2];
-  const float z[4] = {0.f, 0.f, 0.f, 0.f};
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == 4 || MODE == 5) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) z[r] = rzero;  // a kernel argument: ptxas cannot fold it into RZ
+  }
 #pragma unroll
   for (int i = 0; i < MT; i++) {
     rm[i][0] = rm[i][1] = 1e30f;
@@ -60,14 +67,14 @@ __global__ void __launch_bounds__(512) bench(float* out, int steps, long long* c
   uint2 bf = bfrag[lane];
 #pragma unroll 4
   for (int s = 0; s < steps; s++) {
-    if (MODE == 1 || MODE == 2) bf = bfrag[(s & 63) * 32 + lane];
+    if (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 6) bf = bfrag[(s & 63) * 32 + lane];
 #pragma unroll
     for (int i = 0; i < MT; i++) {
-      if (MODE == 0) {
+      if (MODE == 0 || MODE == 6) {
         mma16816(c[i], a[i], bf.x, bf.y, c[i]);
       } else {
         mma16816(c[i], a[i], bf.x, bf.y, z);
-        if (MODE == 1 || MODE == 3) {
+        if (MODE == 1 || MODE == 3 || MODE == 4) {
           rm[i][0] = fmin3(rm[i][0], c[i][0], c[i][1]);
           rm[i][1] = fmin3(rm[i][1], c[i][2], c[i][3]);
         } else {
@@ -99,13 +106,13 @@ static void run(const char* name, int warps_per_sm, int sms) {
   const int steps = 1 << 14;
   const int threads = warps_per_sm * 32;  // one CTA per SM: residency is not in question
   const int ctas_per_sm = 1;
-  bench<MODE, MT><<<sms * ctas_per_sm, threads>>>(out, steps, cyc);
+  bench<MODE, MT><<<sms * ctas_per_sm, threads>>>(out, steps, cyc, 0.0f);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0));
-  bench<MODE, MT><<<sms * ctas_per_sm, threads>>>(out, steps, cyc);
+  bench<MODE, MT><<<sms * ctas_per_sm, threads>>>(out, steps, cyc, 0.0f);
   CK(cudaEventRecord(e1));
   CK(cudaEventSynchronize(e1));
   float ms = 0;
@@ -131,6 +138,9 @@ int main() {
   for (int w : {4, 8, 16}) run<0, 4>("hmma chained", w, sms);
   for (int w : {4, 8, 16}) run<2, 4>("hmma zeroC + lds", w, sms);
   for (int w : {4, 8, 16}) run<3, 4>("hmma zeroC + 2 fmnmx3 (regs)", w, sms);
+  for (int w : {8, 16}) run<6, 4>("hmma chained + lds", w, sms);
+  for (int w : {8, 16}) run<5, 4>("hmma regzeroC + lds", w, sms);
+  for (int w : {8, 16}) run<4, 4>("hmma regzeroC + lds + 2 fmnmx3", w, sms);
   for (int w : {4, 8, 12, 16}) run<1, 4>("hmma zeroC + lds + 2 fmnmx3", w, sms);
   for (int w : {4, 8, 12, 16}) run<1, 2>("hmma zeroC + lds + 2 fmnmx3", w, sms);
   return 0;

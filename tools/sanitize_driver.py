@@ -23,4 +23,27 @@ ga.group_point(pc, i); ga.select_top_k(3, torch.rand(2, 9, 50, device=dev))
 ga.chamfer_all_pairs(cl(5, 300)); ga.chamfer_per_cloud(d1.detach(), d2.detach())
 defense.get_outlier_pc_inlier_pc(pc, torch.rand(2, 700, device=dev), 0.5)
 h = torch.rand(2, 64, 3); ga.nn_distance(h, h); ga.knn_dists(h, 3)
+# round-1 additions: tensor-core forward variants (HMMA grid / persistent, tcgen05), both gradient kernels,
+# the graph replay of the host entry point
+from geometric_adv_b200 import _lib
+import ctypes
+lib = _lib.load()
+for v in (20, 21, 22):
+    lib.ga_set_tuning(0, v)
+    for (b, n, m) in [(2, 300, 517), (3, 2048, 2048)]:
+        ga.nn_distance(cl(b, n), cl(b, m))
+lib.ga_set_tuning(0, 0)
+x1, x2 = cl(3, 700).requires_grad_(True), cl(3, 900).requires_grad_(True)
+for kern in (0, 1):
+    lib.ga_set_tuning(14, kern)
+    d1, i1, d2, i2 = ga.nn_distance(x1, x2)
+    (d1.mean() + d2.mean()).backward()
+lib.ga_set_tuning(14, 0)
+b, n = 24, 1024
+hb = [torch.rand(b, n, 3).pin_memory() - 0.5, torch.rand(b, n, 3).pin_memory() - 0.5, torch.rand(b, n).pin_memory(),
+      torch.rand(b, n).pin_memory(), torch.empty(b, n).pin_memory(), torch.empty(b, n, dtype=torch.int32).pin_memory(),
+      torch.empty(b, n).pin_memory(), torch.empty(b, n, dtype=torch.int32).pin_memory(),
+      torch.empty(b, n, 3).pin_memory(), torch.empty(b, n, 3).pin_memory()]
+for _ in range(3):
+    _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, n, *[ctypes.c_void_p(x.data_ptr()) for x in hb], 0))
 torch.cuda.synchronize(); print("driver ok")
