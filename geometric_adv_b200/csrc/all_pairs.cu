@@ -11,7 +11,9 @@
 // Same filter-and-refine search as nn_distance_fwd.cu, so every per-point distance
 // is bit-identical to the reference arithmetic; the per-cloud mean uses a fixed
 // summation tree (the reference's reduce_mean order is unpinned: tolerance 1e-6).
-#include "nn_search.cuh"
+#include <atomic>
+
+#include "nn_mma.cuh"
 
 namespace ga {
 
@@ -79,12 +81,112 @@ __global__ void __launch_bounds__(PairCfg::kThreads) all_pairs_directed_kernel(c
   }
 }
 
+
+// ---- tensor-core variant (default for clouds of 256..2048 points) ---------------------------------
+// Same decomposition, filter scan of nn_mma.cuh: 8 warps per CTA, the target cloud staged once as
+// pair-SoA + B fragments (96 KB, two CTAs per SM), every warp takes the 64-query jobs
+// warp, warp + 8, ... of each source cloud.  Per-point distances are the same bits as in every other
+// forward kernel; the per-cloud sum runs over (job, lane slot) in a fixed order.
+constexpr int kPairMmaWarps = 8;
+constexpr int kPairMmaCH = 2048;
+constexpr size_t kPairMmaOffRed = (size_t)kPairMmaCH * 16 + (size_t)kPipeU * 32;
+constexpr size_t kPairMmaOffB = kPairMmaOffRed + 32 * 4;
+constexpr size_t kPairMmaOffCnt = kPairMmaOffB + (size_t)kPairMmaCH * 32;
+constexpr size_t kPairMmaOffTile = kPairMmaOffCnt + (size_t)kPairMmaWarps * kMmaQW * 4;
+constexpr size_t kPairMmaSmem = kPairMmaOffTile + (size_t)kPairMmaWarps * kMmaQW * 4;
+
+// One 64-query job: returns the sum of this lane's (up to two) exact distances.  Not inlined: inside
+// the caller's loops ptxas serialises the HMMAs of the scan on one accumulator quad (see persist_job).
+template <int MODE>
+__device__ __noinline__ float pair_job(const float* __restrict__ qpts, const float* __restrict__ tpts, int n, int qbase,
+                                       const float4* __restrict__ tgt, const uint4* __restrict__ bfrag, float bm,
+                                       int* wcnt, unsigned short* wtile) {
+  const int lane = threadIdx.x & 31;
+  MmaRows R;
+  mma_load_rows(R, qpts, n, qbase, lane);
+  QueryState<2> s;
+  mma_init_queries<MODE>(s, qpts, n, qbase, tpts, lane);
+  float mrun[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
+  mma_chunk<MODE>(R, s, mrun, tgt, bfrag, 0, n, n, bm, wcnt, wtile, lane);
+  float part = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    if (!s.valid[j]) continue;
+    float d;
+    int i;
+    finish_query<2>(s, j, d, i);
+    part += d;
+  }
+  return part;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPairMmaWarps * 32, 2) all_pairs_directed_mma_kernel(const PairArgs a) {
+  constexpr int THREADS = kPairMmaWarps * 32, T = kMmaT;
+  extern __shared__ float4 smem_f4[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
+  float4* tgt = smem_f4;
+  float* red = reinterpret_cast<float*>(smem + kPairMmaOffRed);
+  uint4* bfrag = reinterpret_cast<uint4*>(smem + kPairMmaOffB);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* wcnt = reinterpret_cast<int*>(smem + kPairMmaOffCnt) + warp * kMmaQW;
+  unsigned short* wtile = reinterpret_cast<unsigned short*>(smem + kPairMmaOffTile) + warp * kMmaQW * 2;
+  const int n = a.n;
+  const int nblk = (a.na + a.ablk - 1) / a.ablk;
+  const int bj = blockIdx.x / nblk;  // target cloud (slow index: neighbours share sources in L2)
+  const int ab = blockIdx.x - bj * nblk;
+  const float* tpts = a.clouds + (size_t)(a.b0 + bj) * n * 3;
+  const float bm = stage_targets<THREADS, T>(tgt, red, tpts, 0, n, (n + T - 1) / T, tid);
+  stage_bfrag<THREADS>(bfrag, tgt, (n + kMmaBlk - 1) / kMmaBlk, n, tid);
+  __syncthreads();
+  const int jobs = (n + kMmaQW - 1) / kMmaQW;
+  const int a_end = min(a.na, (ab + 1) * a.ablk);
+  for (int ai = ab * a.ablk; ai < a_end; ai++) {
+    const float* qpts = a.clouds + (size_t)(a.a0 + ai) * n * 3;
+    float part = 0.0f;
+    for (int job = warp; job < jobs; job += kPairMmaWarps)
+      part += pair_job<MODE>(qpts, tpts, n, job * kMmaQW, tgt, bfrag, bm, wcnt, wtile);
+    // fixed tree: lanes by xor-shuffle, then warps in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();  // red[] free (staging / previous cloud done)
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kPairMmaWarps; w++) t += red[w];
+      float* o = a.out + (long long)ai * a.stride_a + (long long)bj * a.stride_b;
+      const float v = t / (float)n;
+      *o = a.accumulate ? *o + v : v;
+    }
+  }
+}
+
+int g_pairs_kernel = 0;  // tuning hook (key 16): 0 auto (tensor-core scan from 256 points), 1 = fp32 filter scan
+
 static int launch_directed(const PairArgs& a, int mode, cudaStream_t st) {
   if (a.na <= 0 || a.nb <= 0) return GA_OK;
   const long long ctas = (long long)a.nb * ((a.na + a.ablk - 1) / a.ablk);
   if (ctas > 0x7fffffffLL) {
     set_error("ga_chamfer_all_pairs: problem too large for one launch");
     return GA_ERR_UNSUPPORTED;
+  }
+  if (g_pairs_kernel != 1 && a.n >= 256 && a.n <= kPairMmaCH) {
+    auto km = mode == GA_MODE_CPU_EXACT ? all_pairs_directed_mma_kernel<GA_MODE_CPU_EXACT>
+                                        : all_pairs_directed_mma_kernel<GA_MODE_GPU_REF>;
+    static std::atomic<unsigned> done_mask[2];
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done_mask[mode].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairMmaSmem));
+      done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
+    km<<<(unsigned)ctas, kPairMmaWarps * 32, kPairMmaSmem, st>>>(a);
+    GA_LAUNCH_CHECK("all_pairs_directed_mma_kernel");
+    return GA_OK;
   }
   auto k = mode == GA_MODE_CPU_EXACT ? all_pairs_directed_kernel<GA_MODE_CPU_EXACT>
                                      : all_pairs_directed_kernel<GA_MODE_GPU_REF>;

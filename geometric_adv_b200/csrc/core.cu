@@ -26,6 +26,7 @@ extern int g_umma_grid;          // nn_distance_fwd_umma.cu
 extern int g_bwd_stage;          // nn_distance_bwd.cu
 extern int g_bwd_kernel;         // nn_distance_bwd.cu
 extern int g_pdl;                // nn_distance_bwd.cu
+extern int g_pairs_kernel;       // all_pairs.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -139,6 +140,10 @@ int ga_set_tuning(int key, int value) {
   if (key == 10) {
     ga::g_host_graph = value;
     ga::g_host_graph_epoch++;
+    return GA_OK;
+  }
+  if (key == 16) {
+    ga::g_pairs_kernel = value;
     return GA_OK;
   }
   if (key == 15) {

@@ -32,109 +32,6 @@ struct MmaCfg {
   static constexpr size_t kSmem = kOffTile + (size_t)kQT * 4;
 };
 
-// The two queries a lane refines and writes: m-tile t = lane&3, rows g = lane>>2 and g+8 of the
-// warp's 64 queries, i.e. local queries 16 t + g + 8 j.
-template <int MODE>
-__device__ __forceinline__ void mma_init_queries(QueryState<2>& s, const float* __restrict__ qpts, int nq, int qbase,
-                                                 const float* __restrict__ tpts, int lane) {
-  const float kInf = __int_as_float(0x7f800000);
-  const int g = lane >> 2, t = lane & 3;
-  const float t0x = __ldg(tpts), t0y = __ldg(tpts + 1), t0z = __ldg(tpts + 2);
-#pragma unroll
-  for (int j = 0; j < 2; j++) {
-    const int qi = qbase + 16 * t + g + 8 * j;
-    s.valid[j] = qi < nq;
-    const int qs = s.valid[j] ? qi : 0;
-    s.qx[j] = __ldg(qpts + (size_t)qs * 3);
-    s.qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
-    s.qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
-    s.qabs[j] = query_abs(s.qx[j], s.qy[j], s.qz[j]);
-    s.ax2[j] = -2.0f * s.qx[j];
-    s.ay2[j] = -2.0f * s.qy[j];
-    s.az2[j] = -2.0f * s.qz[j];
-    s.d0[j] = sqdist<MODE>(t0x, t0y, t0z, s.qx[j], s.qy[j], s.qz[j]);
-    s.best[j] = kInf;
-    s.besti[j] = 0;
-    s.m1g[j] = kInf;
-  }
-}
-
-// One staged chunk (targets [c0, c0 + cn) of a cloud with nt points) for one warp: tensor-core
-// scan, per-query lists of the qualifying tiles, exact refine.  mrun: running row minima of h over
-// the chunks seen so far (same value in the 4 lanes of a quad); wcnt / wtile: this warp's lists.
-template <int MODE>
-__device__ __forceinline__ void mma_chunk(const MmaRows& R, QueryState<2>& s, float (&mrun)[8],
-                                          const float4* __restrict__ tgt, const uint4* __restrict__ bfrag, int c0, int nt,
-                                          int cn, float bm_run, int* __restrict__ wcnt,
-                                          unsigned short* __restrict__ wtile, int lane) {
-  constexpr int T = kMmaT;
-  const int g = lane >> 2, t = lane & 3;
-  const int ntile = (cn + T - 1) / T;
-  const int nblk = (cn + kMmaBlk - 1) / kMmaBlk;
-  wcnt[16 * t + g] = 0;
-  wcnt[16 * t + g + 8] = 0;
-  __syncwarp();
-
-  MmaTrack tr;
-  mma_scan(R, reinterpret_cast<const uint2*>(bfrag), nblk, lane, tr);
-
-  // Row minimum over the quad, window, and the qualifying tiles of this lane -> per-query lists.
-  float mythr[2] = {0.0f, 0.0f};
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    float m = tr.c1[r];
-    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    mrun[r] = fminf(mrun[r], m);
-    const float thr = mrun[r] + mma_window(R.qabs[r], bm_run);
-    if (t == (r >> 1)) mythr[r & 1] = thr;
-    const int ql = 16 * (r >> 1) + g + 8 * (r & 1);
-    if (!(tr.c1[r] > thr)) {
-      const int slot = atomicAdd(&wcnt[ql], 1);
-      if (slot < 2) wtile[2 * ql + slot] = (unsigned short)mma_key_tile(tr.c1[r], t);
-    }
-    if (!(tr.c2[r] > thr)) {
-      const int slot = atomicAdd(&wcnt[ql], 1);
-      if (slot < 2) wtile[2 * ql + slot] = (unsigned short)mma_key_tile(tr.c2[r], t);
-    }
-    if (!(tr.c3[r] > thr)) atomicAdd(&wcnt[ql], 3);  // a third tile of this lane: exact scan
-  }
-  __syncwarp();
-
-  int cnt[2], ta[2], tb[2];
-#pragma unroll
-  for (int j = 0; j < 2; j++) {
-    const int ql = 16 * t + g + 8 * j;
-    cnt[j] = wcnt[ql];
-    ta[j] = wtile[2 * ql];
-    tb[j] = wtile[2 * ql + 1];
-    // a tile id beyond the staged tiles can only come from padding under a non-finite window
-    if ((cnt[j] >= 1 && ta[j] >= ntile) || (cnt[j] >= 2 && tb[j] >= ntile)) cnt[j] = 3;
-  }
-  refine_tiles<MODE>(s, tgt, c0, nt, ntile, cnt, ta, tb, mythr);
-  __syncwarp();  // lists are reused by the next chunk / job
-}
-
-__device__ __forceinline__ void mma_write(const QueryState<2>& s, int qbase, int lane, float* __restrict__ odist,
-                                          int* __restrict__ oidx, float* __restrict__ mdist, int* __restrict__ midx,
-                                          size_t moff) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int j = 0; j < 2; j++) {
-    if (!s.valid[j]) continue;
-    const int qi = qbase + 16 * t + g + 8 * j;
-    float d;
-    int i;
-    finish_query<2>(s, j, d, i);
-    odist[qi] = d;
-    oidx[qi] = i;
-    if (mdist != nullptr) {
-      mdist[moff + qi] = d;
-      midx[moff + qi] = i;
-    }
-  }
-}
-
 template <class Cfg, int MODE, int MINB>
 __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const FwdArgs a) {
   constexpr int THREADS = Cfg::kThreads, QT = Cfg::kQT, CH = Cfg::kCH, T = kMmaT;
