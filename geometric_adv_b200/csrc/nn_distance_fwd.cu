@@ -267,6 +267,7 @@ static int launch_fwd(const FwdArgs& a, int mode, cudaStream_t st) {
 int g_fwd_variant = 0;  // tuning hook (ga_set_tuning): 0 = default
 int launch_fwd_mma(const FwdArgs& a, int mode, cudaStream_t st);          // nn_distance_fwd_mma.cu
 int launch_fwd_mma_persist(const FwdArgs& a, int mode, cudaStream_t st);  // nn_distance_fwd_mma.cu
+int launch_fwd_mma_balanced(const FwdArgs& a, int mode, cudaStream_t st); // nn_distance_fwd_mma.cu
 int launch_fwd_umma(const FwdArgs& a, int mode, cudaStream_t st);         // nn_distance_fwd_umma.cu
 bool fwd_umma_supported(int n, int m);                                    // nn_distance_fwd_umma.cu
 
@@ -335,6 +336,7 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   if (variant == 20) return launch_fwd_mma(a, mode, st);
   if (variant == 21) return launch_fwd_mma_persist(a, mode, st);
   if (variant == 22) return launch_fwd_umma(a, mode, st);
+  if (variant == 23) return launch_fwd_mma_balanced(a, mode, st);
   switch (variant) {
 #define GA_FWD_CASE(ID, TH, QQ, TT, CC)                                                          \
   case ID: {                                                                                     \

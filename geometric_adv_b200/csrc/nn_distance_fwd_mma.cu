@@ -205,6 +205,229 @@ __global__ void __launch_bounds__(kPersistWarps * 32, 1)
   }
 }
 
+// ---- balanced persistent variant (23) ----------------------------------------------------------
+// Variant 21 balances whole 64-query jobs: 21.6 jobs for 16 warps is a full round plus a round of
+// lone, latency-bound warps.  Here the unit of work is (job, 128-target block): a super-step's units
+// are cut into 16 equal contiguous warp ranges, so a job may be scanned by several consecutive
+// warps.  Keys carry the whole tile number (6 bits, mma_window_wide), every warp reduces its tracks
+// over the quad (quad_merge) and, if it does not hold the job's last block, publishes the 64 x 3 row
+// keys (768 B) in shared memory; the warp that holds the last block merges the published parts into
+// its own, builds the candidate lists and refines.  A warp first publishes (at most one part), then
+// runs its whole jobs, then the job it has to merge: nobody waits for a part that is not yet queued
+// for publication at the very start of a peer's range.
+constexpr size_t kBalOffPub = kPersistOffCnt;                                   // [16][8][24] float
+constexpr size_t kBalOffFlag = kBalOffPub + (size_t)kPersistWarps * 8 * 24 * 4;  // [16] int
+constexpr size_t kBalOffDesc = kBalOffFlag + 64;                                 // [16][16] int: per-warp part descriptor
+constexpr size_t kBalSmem = kBalOffDesc + (size_t)kPersistWarps * 16 * 4;
+
+struct BalSeg {  // one cloud of a super-step, as read back from the control block
+  int batch, rev, firstq, njobs, nblk;
+};
+
+// Scan blocks [blk0, blk1) of one job; publish, or merge the earlier parts and finish the job.
+// The part is described by 12 words in shared memory (written by the caller, read back here with
+// volatile loads when they are needed): with a dozen scalar arguments live across the scan ptxas
+// falls back to one accumulator quad and a NOP after most HMMAs.
+//   d[0] batch, [1] direction, [2] first query, [3] blk0, [4] blk1, [5] blocks of the job,
+//   [6] first warp holding a part of the job, [7] units of the super-step, [8] generation,
+//   [9] max |target coordinate| (float bits), [10] staged buffer
+template <int MODE>
+__device__ __noinline__ void balanced_part(const FwdArgs& a, const volatile int* d, unsigned char* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  float* pub = reinterpret_cast<float*>(smem + kBalOffPub);
+  volatile int* flags = reinterpret_cast<volatile int*>(smem + kBalOffFlag);
+  const bool rev = d[1] != 0;
+  const int nq = rev ? a.m : a.n;
+  const int nt = rev ? a.n : a.m;
+  const int qbase = d[2];
+  const float* qpts = (rev ? a.xyz2 : a.xyz1) + (size_t)d[0] * nq * 3;
+  const unsigned char* bufp = smem + (d[10] ? kPersistBuf : 0);
+  const float4* tgt = reinterpret_cast<const float4*>(bufp);
+  const uint2* bfrag = reinterpret_cast<const uint2*>(bufp + (size_t)kPersistCH * 16 + (size_t)kPipeU * 32);
+  MmaRows R;
+  mma_load_rows(R, qpts, nq, qbase, lane);
+  MmaTrack tr;
+  mma_scan_range<6>(R, bfrag, d[3], d[4], lane, tr);
+  quad_merge(tr);
+  const int gen = d[8];
+  if (d[4] < d[5]) {  // not the last block of the job: hand the row keys to the warp that has it
+    if (t == 0) {
+      float* dst = pub + (size_t)(warp * 8 + g) * 24;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        dst[3 * r] = tr.c1[r];
+        dst[3 * r + 1] = tr.c2[r];
+        dst[3 * r + 2] = tr.c3[r];
+      }
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) flags[warp] = gen;
+    return;
+  }
+  const int utot = d[7];
+  for (int pw = d[6]; pw < warp; pw++) {  // earlier parts of this job (blk0 > 0)
+    // a warp whose range is empty (fewer units than warps) holds no part and never publishes
+    if ((int)((long long)utot * pw / kPersistWarps) == (int)((long long)utot * (pw + 1) / kPersistWarps)) continue;
+    if (lane == 0)
+      while (flags[pw] != gen) {
+      }
+    __syncwarp();
+    __threadfence_block();
+    const volatile float* src = pub + (size_t)(pw * 8 + g) * 24;
+#pragma unroll
+    for (int r = 0; r < 8; r++) merge3(tr.c1[r], tr.c2[r], tr.c3[r], src[3 * r], src[3 * r + 1], src[3 * r + 2]);
+  }
+  // this lane's two queries are rows 2t and 2t+1 of its quad
+  const int batch = d[0];
+  const float bm = __int_as_float(d[9]);
+  const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
+  QueryState<2> s;
+  mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane);
+  const int ntile = (nt + kMmaT - 1) / kMmaT;
+  int cnt[2], ta[2], tb[2];
+  float thr[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const float k1 = t == 0 ? tr.c1[j] : (t == 1 ? tr.c1[2 + j] : (t == 2 ? tr.c1[4 + j] : tr.c1[6 + j]));
+    const float k2 = t == 0 ? tr.c2[j] : (t == 1 ? tr.c2[2 + j] : (t == 2 ? tr.c2[4 + j] : tr.c2[6 + j]));
+    const float k3 = t == 0 ? tr.c3[j] : (t == 1 ? tr.c3[2 + j] : (t == 2 ? tr.c3[4 + j] : tr.c3[6 + j]));
+    const float qa = t == 0 ? R.qabs[j] : (t == 1 ? R.qabs[2 + j] : (t == 2 ? R.qabs[4 + j] : R.qabs[6 + j]));
+    thr[j] = k1 + mma_window_wide(qa, bm);
+    int c = !(k1 > thr[j]) ? 1 : 0;
+    c += !(k2 > thr[j]) ? 1 : 0;
+    if (!(k3 > thr[j])) c = 3;
+    ta[j] = __float_as_int(k1) & 63;
+    tb[j] = __float_as_int(k2) & 63;
+    // a tile beyond the staged tiles can only come from padding / sentinels under a non-finite window
+    if ((c >= 1 && ta[j] >= ntile) || (c >= 2 && tb[j] >= ntile)) c = 3;
+    cnt[j] = c;
+  }
+  refine_tiles<MODE>(s, tgt, 0, nt, ntile, cnt, ta, tb, thr);
+  mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
+            rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPersistWarps * 32, 1)
+    nn_fwd_mma_balanced_kernel(const FwdArgs a, const int wt1, const int wt2, const long long J) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  extern __shared__ float4 smem_f4[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
+  float* red = reinterpret_cast<float*>(smem + kPersistOffRed);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  volatile int* ctl = reinterpret_cast<volatile int*>(smem + kPersistOffCtr + 16);
+  long long* jcur = reinterpret_cast<long long*>(smem + kPersistOffCtr + 64);
+  float* pub = reinterpret_cast<float*>(smem + kBalOffPub);
+  volatile int* flags = reinterpret_cast<volatile int*>(smem + kBalOffFlag);
+  volatile int* desc = reinterpret_cast<volatile int*>(smem + kBalOffDesc) + warp * 16;
+
+  auto stage = [&](int buf, int batch, bool rev) {  // this warp's 128-target block of a target cloud
+    const int nt = rev ? a.n : a.m;
+    const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
+    float4* tgt = reinterpret_cast<float4*>(smem + buf * kPersistBuf);
+    uint4* bfrag = reinterpret_cast<uint4*>(smem + buf * kPersistBuf + (size_t)kPersistCH * 16 + (size_t)kPipeU * 32);
+    float lmax = 0.0f;
+    if (warp * kMmaBlk < nt) lmax = stage_block_warp(tgt, bfrag, tpts, nt, warp, lane);
+    lmax = warp_max(lmax);
+    if (lane == 0) red[buf * 16 + warp] = lmax;
+  };
+
+  if (tid < kPersistWarps) flags[tid] = 0;
+  if (tid == 0) *jcur = J * blockIdx.x / gridDim.x;
+  for (int gen = 1;; gen++) {
+    if (tid == 0) {
+      const long long jpb = (long long)wt1 + wt2;
+      const long long j1 = J * (blockIdx.x + 1) / gridDim.x;
+      long long j = *jcur;
+      ctl[8] = j >= j1;
+      for (int sgm = 0; sgm < 2; sgm++) {
+        int batch = 0, rev = 0, firstq = 0, njobs = 0;
+        if (j < j1) {
+          batch = (int)(j / jpb);
+          const long long r = j - (long long)batch * jpb;
+          rev = r >= wt1;
+          const long long sbeg = (long long)batch * jpb + (rev ? wt1 : 0);
+          const long long send = sbeg + (rev ? wt2 : wt1);
+          const long long pend = send < j1 ? send : j1;
+          firstq = (int)(j - sbeg) * kMmaQW;
+          njobs = (int)(pend - j);
+          j = pend;
+        }
+        ctl[4 * sgm] = batch;
+        ctl[4 * sgm + 1] = rev;
+        ctl[4 * sgm + 2] = firstq;
+        ctl[4 * sgm + 3] = njobs;
+      }
+      *jcur = j;
+    }
+    __syncthreads();
+    if (ctl[8]) break;
+    stage(0, ctl[0], ctl[1] != 0);
+    if (ctl[7] > 0) stage(1, ctl[4], ctl[5] != 0);
+    __syncthreads();
+
+    BalSeg sg[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      sg[i].batch = ctl[4 * i];
+      sg[i].rev = ctl[4 * i + 1];
+      sg[i].firstq = ctl[4 * i + 2];
+      sg[i].njobs = ctl[4 * i + 3];
+      sg[i].nblk = ((sg[i].rev ? a.n : a.m) + kMmaBlk - 1) / kMmaBlk;
+    }
+    const int ua = sg[0].njobs * sg[0].nblk;            // units of cloud A; cloud B follows
+    const int utot = ua + sg[1].njobs * sg[1].nblk;
+    auto wstart = [&](int w) { return (int)((long long)utot * w / kPersistWarps); };
+    const int u0 = wstart(warp), u1 = wstart(warp + 1);
+    float bmv[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int w = 0; w < 16; w++) {
+      bmv[0] = fmaxf(bmv[0], red[w]);
+      bmv[1] = fmaxf(bmv[1], red[16 + w]);
+    }
+    // pass 0: the part to publish (range ends inside a job); pass 1: whole jobs; pass 2: the job to merge
+    for (int pass = 0; pass < 3; pass++) {
+      int u = u0;
+      while (u < u1) {
+        const int i = u >= ua ? 1 : 0;
+        const int ul = u - (i ? ua : 0);
+        const int jo = ul / sg[i].nblk, blk0 = ul - jo * sg[i].nblk;
+        const int blk1 = min(sg[i].nblk, blk0 + (u1 - u));
+        const int kind = blk1 < sg[i].nblk ? 0 : (blk0 == 0 ? 1 : 2);
+        if (kind == pass) {
+          int fw = warp;  // warp that holds block 0 of this job
+          if (blk0 > 0) {
+            const int ub = u - blk0;
+            fw = (int)(((long long)ub * kPersistWarps) / utot);
+            while (fw + 1 < kPersistWarps && wstart(fw + 1) <= ub) fw++;
+            while (fw > 0 && wstart(fw) > ub) fw--;
+          }
+          if (lane == 0) {
+            desc[0] = sg[i].batch;
+            desc[1] = sg[i].rev;
+            desc[2] = sg[i].firstq + jo * kMmaQW;
+            desc[3] = blk0;
+            desc[4] = blk1;
+            desc[5] = sg[i].nblk;
+            desc[6] = fw;
+            desc[7] = utot;
+            desc[8] = gen;
+            desc[9] = __float_as_int(i ? bmv[1] : bmv[0]);
+            desc[10] = i;
+          }
+          __syncwarp();
+          balanced_part<MODE>(a, desc, smem);
+          __syncwarp();
+        }
+        u += blk1 - blk0;
+      }
+    }
+    __syncthreads();  // buffers, control block and publish slots are free again
+  }
+}
+
 // Debug / evidence: the raw tensor-core filter values h(q,t) of one cloud pair (n queries,
 // m <= 2048 targets), out[q*m + t].  Uses the same staging, fragments and column map as the
 // product kernel; tests compare it with the fp64 value to check the layout and the bound e2.
@@ -299,6 +522,32 @@ int launch_fwd_mma_persist(const FwdArgs& a, int mode, cudaStream_t st) {
   if (grid > J) grid = J;
   k<<<(unsigned)grid, kPersistWarps * 32, kPersistSmem, st>>>(a, wt1, wt2, J);
   GA_LAUNCH_CHECK("nn_fwd_mma_persist_kernel");
+  return GA_OK;
+}
+
+int launch_fwd_mma_balanced(const FwdArgs& a, int mode, cudaStream_t st) {
+  if (a.n > kPersistCH || a.m > kPersistCH) {
+    set_error("nn_fwd_mma_balanced_kernel: clouds of at most %d points", kPersistCH);
+    return GA_ERR_UNSUPPORTED;
+  }
+  const int wt1 = (a.n + kMmaQW - 1) / kMmaQW, wt2 = (a.m + kMmaQW - 1) / kMmaQW;
+  const long long J = (long long)a.b * (wt1 + wt2);
+  if (J <= 0) return GA_OK;
+  auto k = mode == GA_MODE_CPU_EXACT ? nn_fwd_mma_balanced_kernel<GA_MODE_CPU_EXACT>
+                                     : nn_fwd_mma_balanced_kernel<GA_MODE_GPU_REF>;
+  {
+    static std::atomic<unsigned> done_mask[2];
+    int dev = 0;
+    GA_CUDA_TRY(cudaGetDevice(&dev));
+    if (!(done_mask[mode].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+      GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBalSmem));
+      done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+    }
+  }
+  long long grid = g_mma_grid > 0 ? g_mma_grid : sm_count();
+  if (grid > J) grid = J;
+  k<<<(unsigned)grid, kPersistWarps * 32, kBalSmem, st>>>(a, wt1, wt2, J);
+  GA_LAUNCH_CHECK("nn_fwd_mma_balanced_kernel");
   return GA_OK;
 }
 

@@ -181,15 +181,20 @@ struct MmaTrack {
 };
 __device__ __forceinline__ int mma_key_tile(float key, int t) { return ((__float_as_int(key) & 15) << 2) + t; }
 
-// Tensor-core filter scan over `nblk` (<= 16) staged blocks.  Lane (g,t) sees, for each of its 8
-// rows, the minimum of h over the 32 contiguous targets [128 blk + 32 t, +32) of every block, i.e.
-// over refine tile 4 blk + t, without any cross-lane traffic.
-__device__ __forceinline__ void mma_scan(const MmaRows& R, const uint2* __restrict__ bfrag, int nblk, int lane,
-                                         MmaTrack& tr) {
+// Tensor-core filter scan over the staged blocks [blk0, blk1) (blk1 <= 16).  Lane (g,t) sees, for each
+// of its 8 rows, the minimum of h over the 32 contiguous targets [128 blk + 32 t, +32) of every block,
+// i.e. over refine tile 4 blk + t, without any cross-lane traffic.  KEYBITS = 4: the key carries the
+// block number (the tile is 4 blk + t, t known from the lane); KEYBITS = 6: it carries the whole tile
+// number 4 blk + t, so that keys of different lanes can be merged (quad_merge; 64 ulp <= 384u s^2 of
+// perturbation: callers use mma_window_wide).
+template <int KEYBITS>
+__device__ __forceinline__ void mma_scan_range(const MmaRows& R, const uint2* __restrict__ bfrag, int blk0, int blk1,
+                                               int lane, MmaTrack& tr) {
+  static_assert(KEYBITS == 4 || KEYBITS == 6, "key layouts");
 #pragma unroll
   for (int r = 0; r < 8; r++) tr.c1[r] = tr.c2[r] = tr.c3[r] = kMmaBig;
 #pragma unroll 1
-  for (int blk = 0; blk < nblk; blk++) {
+  for (int blk = blk0; blk < blk1; blk++) {
     float rm[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) rm[r] = kMmaBig;
@@ -205,12 +210,45 @@ __device__ __forceinline__ void mma_scan(const MmaRows& R, const uint2* __restri
         rm[2 * i + 1] = fmin3(rm[2 * i + 1], c[2], c[3]);
       }
     }
+    const int id = KEYBITS == 4 ? blk : 4 * blk + (lane & 3);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      const float key = __int_as_float((__float_as_int(rm[r]) & ~15) | blk);
+      const float key = __int_as_float((__float_as_int(rm[r]) & ~((1 << KEYBITS) - 1)) | id);
       tr.c3[r] = fminf(tr.c3[r], fmaxf(tr.c2[r], key));
       tr.c2[r] = fminf(tr.c2[r], fmaxf(tr.c1[r], key));
       tr.c1[r] = fminf(tr.c1[r], key);
+    }
+  }
+}
+__device__ __forceinline__ void mma_scan(const MmaRows& R, const uint2* __restrict__ bfrag, int nblk, int lane,
+                                         MmaTrack& tr) {
+  mma_scan_range<4>(R, bfrag, 0, nblk, lane, tr);
+}
+
+// Window for 6-bit keys: 2 e0 + 2 (e2 + 384u) = 1458u < 2048u = 2^-13 s^2 (see the header).
+__device__ __forceinline__ float mma_window_wide(float qabs, float bm) {
+  const float s = (qabs + bm) * 1.0001f;
+  return fmaf(s * s, 1.220703125e-04f /* 2^-13 */, 1e-35f);
+}
+
+// (a1 <= a2 <= a3) := the three smallest of two sorted triples.
+__device__ __forceinline__ void merge3(float& a1, float& a2, float& a3, float b1, float b2, float b3) {
+  const float lo = fmaxf(a1, b1), hi = fminf(a2, b2);
+  a3 = fminf(fmaxf(lo, hi), fminf(a3, b3));
+  a2 = fminf(lo, hi);
+  a1 = fminf(a1, b1);
+}
+
+// After this every lane of a quad holds, per row, the three smallest 6-bit keys over the quad's four
+// tile columns.
+__device__ __forceinline__ void quad_merge(MmaTrack& tr) {
+#pragma unroll
+  for (int m = 1; m <= 2; m <<= 1) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const float b1 = __shfl_xor_sync(0xffffffffu, tr.c1[r], m), b2 = __shfl_xor_sync(0xffffffffu, tr.c2[r], m),
+                  b3 = __shfl_xor_sync(0xffffffffu, tr.c3[r], m);
+      merge3(tr.c1[r], tr.c2[r], tr.c3[r], b1, b2, b3);
     }
   }
 }

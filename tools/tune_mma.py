@@ -49,8 +49,8 @@ for (b, n, m) in [(50, 2048, 2048), (10, 2048, 2048), (512, 2048, 2048), (50, 20
         lib.ga_nn_distance_fwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()), p(i1.data_ptr()),
                                p(d2.data_ptr()), p(i2.data_ptr()), 0, p(st))
 
-    for name, v, cfg in [("default", 0, 0), ("fp32_v1", 1, 0)] + [("mma_cfg%d" % c, 20, c) for c in (1, 4, 5)] + [("mma_persist", 21, 0), ("umma", 22, 0)]:
-        if v in (21, 22) and max(n, m) > 2048:
+    for name, v, cfg in [("default", 0, 0), ("fp32_v1", 1, 0)] + [("mma_cfg%d" % c, 20, c) for c in (1, 4, 5)] + [("mma_persist", 21, 0), ("mma_balanced", 23, 0), ("umma", 22, 0)]:
+        if v in (21, 22, 23) and max(n, m) > 2048:
             continue
         lib.ga_set_tuning(0, v)
         lib.ga_set_tuning(7, cfg)
