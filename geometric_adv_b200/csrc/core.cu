@@ -22,6 +22,7 @@ extern int g_bwd_split;       // nn_distance_bwd.cu
 extern int g_host_graph;         // host_api.cu
 extern int g_host_graph_chunks;  // host_api.cu
 extern int g_host_graph_epoch;   // host_api.cu
+extern int g_host_graph_mirror;  // host_api.cu
 extern int g_umma_grid;          // nn_distance_fwd_umma.cu
 extern int g_bwd_stage;          // nn_distance_bwd.cu
 extern int g_bwd_kernel;         // nn_distance_bwd.cu
@@ -139,6 +140,11 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 10) {
     ga::g_host_graph = value;
+    ga::g_host_graph_epoch++;
+    return GA_OK;
+  }
+  if (key == 17) {
+    ga::g_host_graph_mirror = value;
     ga::g_host_graph_epoch++;
     return GA_OK;
   }

@@ -162,7 +162,9 @@ static bool device_can_touch(const void* p) {
 // gradients after the backward.  Pageable buffers never take this path.
 int g_host_graph = 0;         // tuning hook (key 10): 0 auto, 1 never replay, 2 capture on first sight
 int g_host_graph_chunks = 0;  // tuning hook (key 11): chunks of the captured pipeline (0 = auto)
-int g_host_graph_epoch = 0;   // bumped by ga_set_tuning(10 | 11): cached graphs of older epochs are dropped
+int g_host_graph_epoch = 0;   // bumped by ga_set_tuning(10 | 11 | 17): cached graphs of older epochs are dropped
+int g_host_graph_mirror = 0;  // tuning hook (key 17): 0 auto, 1 = always copy dist/idx, 2 = always let the forward
+                              // kernel write them straight to the pinned host buffers inside the replayed graph
 
 struct HostGraph {
   cudaGraphExec_t exec = nullptr;
@@ -191,6 +193,7 @@ struct FwdBwdBufs {
   int *idx1, *idx2;
   float *d_x1, *d_x2, *d_g1, *d_g2, *d_d1, *d_d2, *d_o1, *d_o2;  // arena
   int *d_i1, *d_i2;
+  bool mirror;  // dist/idx host buffers are device-accessible: the forward kernel mirrors its outputs there
 };
 
 static int pipeline_lanes(int nchunk) {
@@ -227,19 +230,28 @@ static int issue_pipeline(const FwdBwdBufs& f, int b, int n, int m, int mode, in
     GA_CUDA_TRY(cudaEventRecord(ev_g[ch], sin));
 
     GA_CUDA_TRY(cudaStreamWaitEvent(sk, ev_x[ch], 0));
-    GA_TRY(ga_nn_distance_fwd(bc, n, m, f.d_x1 + o1 * 3, f.d_x2 + o2 * 3, f.d_d1 + o1, f.d_i1 + o1, f.d_d2 + o2,
-                              f.d_i2 + o2, mode, (ga_stream_t)sk));
+    if (f.mirror) {
+      // results stream over PCIe while the search runs (1.6 MB of posted writes spread over the kernel)
+      GA_TRY(nn_distance_fwd_mirrored(bc, n, m, f.d_x1 + o1 * 3, f.d_x2 + o2 * 3, f.d_d1 + o1, f.d_i1 + o1, f.d_d2 + o2,
+                                      f.d_i2 + o2, f.dist1 + o1, f.idx1 + o1, f.dist2 + o2, f.idx2 + o2, mode,
+                                      (ga_stream_t)sk));
+    } else {
+      GA_TRY(ga_nn_distance_fwd(bc, n, m, f.d_x1 + o1 * 3, f.d_x2 + o2 * 3, f.d_d1 + o1, f.d_i1 + o1, f.d_d2 + o2,
+                                f.d_i2 + o2, mode, (ga_stream_t)sk));
+    }
     GA_CUDA_TRY(cudaEventRecord(ev_f[ch], sk));
     GA_CUDA_TRY(cudaStreamWaitEvent(sk, ev_g[ch], 0));
     GA_TRY(ga_nn_distance_bwd(bc, n, m, f.d_x1 + o1 * 3, f.d_x2 + o2 * 3, f.d_g1 + o1, f.d_i1 + o1, f.d_g2 + o2,
                               f.d_i2 + o2, f.d_o1 + o1 * 3, f.d_o2 + o2 * 3, (ga_stream_t)sk));
     GA_CUDA_TRY(cudaEventRecord(ev_b[ch], sk));
 
-    GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_f[ch], 0));
-    GA_CUDA_TRY(cudaMemcpyAsync(f.dist1 + o1, f.d_d1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
-    GA_CUDA_TRY(cudaMemcpyAsync(f.idx1 + o1, f.d_i1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
-    GA_CUDA_TRY(cudaMemcpyAsync(f.dist2 + o2, f.d_d2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
-    GA_CUDA_TRY(cudaMemcpyAsync(f.idx2 + o2, f.d_i2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
+    if (!f.mirror) {
+      GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_f[ch], 0));
+      GA_CUDA_TRY(cudaMemcpyAsync(f.dist1 + o1, f.d_d1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
+      GA_CUDA_TRY(cudaMemcpyAsync(f.idx1 + o1, f.d_i1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
+      GA_CUDA_TRY(cudaMemcpyAsync(f.dist2 + o2, f.d_d2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
+      GA_CUDA_TRY(cudaMemcpyAsync(f.idx2 + o2, f.d_i2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
+    }
     GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_b[ch], 0));
     GA_CUDA_TRY(cudaMemcpyAsync(f.gx1 + o1 * 3, f.d_o1 + o1 * 3, c1 * 12, cudaMemcpyDeviceToHost, sout));
     GA_CUDA_TRY(cudaMemcpyAsync(f.gx2 + o2 * 3, f.d_o2 + o2 * 3, c2 * 12, cudaMemcpyDeviceToHost, sout));
@@ -445,8 +457,14 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
         int nc = g_host_graph_chunks > 0 ? g_host_graph_chunks : (traffic >= ((size_t)4 << 20) ? 2 : 1);
         nc = nc < 1 ? 1 : (nc > 8 ? 8 : nc);
         if (nc > b) nc = b;
+        // Small steps (one chunk): the forward kernel writes dist/idx straight into the pinned host buffers
+        // while it searches, which saves four copy nodes (B=10: 92 -> 81 us).  From 4 MB on the posted
+        // PCIe writes slow the kernel more than the copies cost (B=50: 208 vs 216 us, B=200: 575 vs 657).
+        const bool mirror = (g_host_graph_mirror == 2 || (g_host_graph_mirror == 0 && traffic < ((size_t)4 << 20))) &&
+                            device_can_touch(dist1) && device_can_touch(idx1) && device_can_touch(dist2) &&
+                            device_can_touch(idx2);
         FwdBwdBufs f = {xyz1, xyz2, grad_dist1, grad_dist2, dist1, dist2, grad_xyz1, grad_xyz2, idx1, idx2,
-                        d_x1, d_x2, d_g1, d_g2, d_d1, d_d2, d_o1, d_o2, d_i1, d_i2};
+                        d_x1, d_x2, d_g1, d_g2, d_d1, d_d2, d_o1, d_o2, d_i1, d_i2, mirror};
         if (capture_pipeline(G, f, b, n, m, mode, nc) != GA_OK) G.failed = true;  // fall through to the direct path
       }
     }

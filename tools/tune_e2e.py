@@ -30,9 +30,11 @@ for (B, N, M) in [(50, 2048, 2048), (10, 2048, 2048), (200, 2048, 2048)]:
 
     key = "b%d" % B
     out[key] = {}
-    for name, k10, k11 in [("direct", 1, 0)] + [("graph_c%d" % c, 0, c) for c in (1, 2, 3, 4, 5, 6, 8)] + [("graph_auto", 0, 0)]:
+    for name, k10, k11, k17 in ([("direct", 1, 0, 0)] + [("graph_c%d_mirror_dist_idx" % c, 0, c, 2) for c in (1, 2, 3, 4)] +
+                                [("graph_c%d_copy_dist_idx" % c, 0, c, 1) for c in (1, 2, 3)] + [("graph_auto", 0, 0, 0)]):
         lib.ga_set_tuning(10, k10)
         lib.ga_set_tuning(11, k11)
+        lib.ga_set_tuning(17, k17)
         for _ in range(5):
             step()
         ts = []
@@ -45,5 +47,6 @@ for (B, N, M) in [(50, 2048, 2048), (10, 2048, 2048), (200, 2048, 2048)]:
         print(key, name, "min %.1f us  med %.1f us" % (ts[0] * 1e6, ts[len(ts) // 2] * 1e6), flush=True)
     lib.ga_set_tuning(10, 0)
     lib.ga_set_tuning(11, 0)
+    lib.ga_set_tuning(17, 0)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune_e2e.json"), "w"), indent=1)
