@@ -35,6 +35,7 @@ SIGNATURES = {
     "ga_nn_distance_fwd_ws": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, C.c_size_t, _p]),
     "ga_nn_distance_fwd_host": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i]),
     "ga_nn_distance_bwd": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ga_nn_distance_fwd_bwd": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "ga_nn_distance_bwd_host": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ga_nn_distance_fwd_bwd_host": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i]),
     "ga_chamfer_per_cloud": (_i, [_i, _i, _i, _p, _p, _p, _p]),

@@ -28,6 +28,7 @@ extern int g_bwd_stage;          // nn_distance_bwd.cu
 extern int g_bwd_kernel;         // nn_distance_bwd.cu
 extern int g_pdl;                // nn_distance_bwd.cu
 extern int g_pairs_kernel;       // all_pairs.cu
+extern int g_tickets;            // nn_distance_fwd_mma.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -46,6 +47,47 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 long long launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
 void note_kernel(const char* name) { t_last_kernel = name; }
+
+unsigned long long next_call_id() {
+  static std::atomic<unsigned long long> g_call{0};
+  return g_call.fetch_add(1, std::memory_order_relaxed) + 1;  // never 0
+}
+
+LastForward& last_forward() {
+  static thread_local LastForward t_last = {};
+  return t_last;
+}
+
+// One 32 KB array per device, allocated and zeroed at the first ticketed launch that is not inside a
+// stream capture (cudaMalloc is not capturable); until then the feature is simply off.
+unsigned long long* ticket_buffer(cudaStream_t st) {
+  static std::atomic<unsigned long long*> g_buf[32];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  unsigned long long* p = g_buf[dev].load(std::memory_order_acquire);
+  if (p != nullptr) return p;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  unsigned long long* fresh = nullptr;
+  if (cudaMalloc(&fresh, sizeof(unsigned long long) * (kTicketSlots + 8)) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (cudaMemset(fresh, 0, sizeof(unsigned long long) * (kTicketSlots + 8)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(fresh);
+    return nullptr;
+  }
+  unsigned long long* expect = nullptr;
+  if (!g_buf[dev].compare_exchange_strong(expect, fresh, std::memory_order_acq_rel)) {
+    cudaFree(fresh);  // another thread was faster
+    return expect;
+  }
+  return fresh;
+}
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -143,6 +185,10 @@ int ga_set_tuning(int key, int value) {
     ga::g_host_graph_epoch++;
     return GA_OK;
   }
+  if (key == 18) {
+    ga::g_tickets = value;
+    return GA_OK;
+  }
   if (key == 17) {
     ga::g_host_graph_mirror = value;
     ga::g_host_graph_epoch++;
@@ -178,6 +224,16 @@ int ga_set_tuning(int key, int value) {
 }
 const char* ga_last_error(void) { return t_err; }
 const char* ga_last_kernel(void) { return t_last_kernel; }
+
+// development: copy (and clear) the 8 debug words behind the completion tickets
+int ga_debug_ticket_stats(unsigned long long* out8) {
+  unsigned long long* t = ga::ticket_buffer(nullptr);
+  if (t == nullptr) return GA_ERR_UNSUPPORTED;
+  GA_CUDA_TRY(cudaDeviceSynchronize());
+  GA_CUDA_TRY(cudaMemcpy(out8, t + ga::kTicketSlots, 64, cudaMemcpyDeviceToHost));
+  GA_CUDA_TRY(cudaMemset(t + ga::kTicketSlots, 0, 64));
+  return GA_OK;
+}
 long long ga_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // tf_nndistance.cpp:51-58

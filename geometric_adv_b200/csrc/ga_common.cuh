@@ -16,6 +16,21 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* where);
 void count_launch(int n = 1);
 void note_kernel(const char* name);
+
+// Completion tickets (core.cu): a small per-device array through which the forward search tells the
+// gradient kernel, per batch element, that its dist/idx rows are final -- see nn_distance_bwd.cu.
+constexpr int kTicketSlots = 4096;  // + 8 words of debug counters behind the slots (ga_debug_ticket_stats)
+unsigned long long* ticket_buffer(cudaStream_t st);  // nullptr if it cannot be provided right now
+unsigned long long next_call_id();
+struct LastForward {  // the calling thread's most recent ticketed forward launch
+  cudaStream_t stream;
+  const int* idx1;
+  const int* idx2;
+  int b, n, m, expected;
+  unsigned long long call_id;
+  unsigned long long* ticket;
+};
+LastForward& last_forward();
 int sm_count();
 
 #define GA_CUDA_TRY(expr)                                   \
@@ -63,6 +78,16 @@ __device__ __forceinline__ float sqdist(float tx, float ty, float tz, float qx, 
   } else {
     return __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
   }
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ int ticket_slot(unsigned long long call_id, int batch) {
+  return (int)((call_id * 2654435761ull + (unsigned long long)batch) & (unsigned long long)(kTicketSlots - 1));
 }
 
 __device__ __forceinline__ float warp_max(float v) {

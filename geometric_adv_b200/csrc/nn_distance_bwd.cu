@@ -38,6 +38,12 @@ struct BwdArgs {
   const int* idx2;
   float* gxyz1;
   float* gxyz2;
+  // completion tickets of the forward launch that wrote idx1 / idx2 (nullptr = wait for the whole grid)
+  const unsigned long long* ticket;
+  unsigned long long call_id;
+  int expected;
+  int ticket_debug;
+  int gd_final;  // fused entry point: the upstream gradients were final before the forward search was launched
 };
 
 // Partner clouds up to this size are staged in shared memory ({x, y, z, grad_dist} per point): the
@@ -368,26 +374,48 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
       if (e < L) pcloud[e] = make_float4(px[u], py[u], pz[u], 0.0f);
     }
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // The index rows of this batch element are final once all of the forward search's CTAs for it have
+  // checked in (completion ticket, written with a release fence behind their stores).  Then the inverse
+  // map below is built while the rest of that grid is still running; otherwise, or when the ticket
+  // never shows up (slot reused by another call), wait for the whole grid as any dependent would.
+  __shared__ int early_flag;
+  if (tid == 0) {
+    int early = 0;
+    if (a.ticket != nullptr) {
+      const volatile unsigned long long* slot = a.ticket + ticket_slot(a.call_id, batch);
+      const unsigned long long want = (a.call_id << 16) | (unsigned long long)a.expected;
+      for (int spin = 0; spin < 400 && !early; spin++) {
+        if (*slot == want) early = 1;
+        else __nanosleep(100);
+      }
+      if (early) __threadfence();  // acquire side: the stores behind the ticket are visible below
+    }
+    early_flag = early;
+    if (a.ticket_debug) {  // development counters: early CTAs, first / last CTA start, last inverse map done
+      unsigned long long* dbg = const_cast<unsigned long long*>(a.ticket) + kTicketSlots;
+      if (early) atomicAdd(dbg + 0, 1ull);
+      atomicAdd(dbg + 1, 1ull);
+      atomicMax(dbg + 5, global_ns());
+      if (blockIdx.x == 0) dbg[6] = global_ns();
+    }
+  }
+  __syncthreads();
+  const bool early = early_flag != 0;
+  if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int e0 = tid; e0 < L; e0 += 4 * T) {
-    float pg[4];
     int pk[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int e = e0 + u * T;
-      const int es = e < L ? e : 0;
-      pg[u] = oth_gd[es];   // plain loads: written by the kernel this grid depends on
-      pk[u] = oth_idx[es];
+      pk[u] = *reinterpret_cast<const volatile int*>(oth_idx + (e < L ? e : 0));  // written by the forward grid
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int e = e0 + u * T;
-      if (e < L) {
-        reinterpret_cast<float*>(pcloud + e)[3] = pg[u];   // same thread wrote x, y, z
-        keys[e] = pk[u];
-      }
+      if (e < L) keys[e] = pk[u];
     }
   }
+  bool gd_staged = false;
 
   for (int k0 = part * K; k0 < P; k0 += a.nparts * K) {
     const int kn = min(K, P - k0);
@@ -433,6 +461,14 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
       if (kk >= 0 && kk < kn) order[start[kk] + atomicAdd(&cnt[kk], 1)] = (unsigned short)e;
     }
     __syncthreads();
+    // upstream gradients: whatever kernel precedes this one on the stream may have written them, so
+    // they are read only behind the grid dependency (a no-op if the early path was not taken)
+    if (!gd_staged) {
+      if (early && !a.gd_final) asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (int e = tid; e < L; e += T) reinterpret_cast<float*>(pcloud + e)[3] = oth_gd[e];
+      gd_staged = true;
+      __syncthreads();
+    }
     // 4. one thread per output point: sort its list, walk it in ascending order
     {
       float ox[PER], oy[PER], oz[PER], gown[PER];
@@ -446,7 +482,7 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
         ox[i] = __ldg(own + (size_t)p * 3);
         oy[i] = __ldg(own + (size_t)p * 3 + 1);
         oz[i] = __ldg(own + (size_t)p * 3 + 2);
-        j2[i] = own_idx[p];
+        j2[i] = *reinterpret_cast<const volatile int*>(own_idx + p);
         gown[i] = own_gd[p];
       }
 #pragma unroll
@@ -506,12 +542,17 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
   }
 }
 
+extern int g_tickets;  // nn_distance_fwd_mma.cu
 int g_pdl = 1;         // tuning hook (key 15): 0 = plain launches (no programmatic dependent launch)
 int g_bwd_kernel = 0;  // tuning hook (key 14): 0 auto (second formulation when it applies), 1 = stable counting sort
 int g_bwd_stage = 1;   // tuning hook (key 13): 0 = gather the partner cloud from global memory (no staging)
 int g_bwd_split = -1;  // tuning hook (key 9): -1 auto, 0 one CTA per cloud, 1 output points split over 4 CTAs
 
 }  // namespace ga
+
+namespace ga {
+static thread_local int t_gd_final = 0;  // set by ga_nn_distance_fwd_bwd around its gradient launch
+}
 
 extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const float* xyz2,
                                   const float* grad_dist1, const int* idx1, const float* grad_dist2,
@@ -544,6 +585,8 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
   a.xyz1 = xyz1; a.xyz2 = xyz2;
   a.gd1 = grad_dist1; a.idx1 = idx1; a.gd2 = grad_dist2; a.idx2 = idx2;
   a.gxyz1 = grad_xyz1; a.gxyz2 = grad_xyz2;
+  a.ticket = nullptr; a.call_id = 0; a.expected = 0; a.ticket_debug = 0;
+  a.gd_final = t_gd_final;
   // Up to one wave of split CTAs: split the output points (measured, 2048-point clouds: B=1 17.4 ->
   // 14.3 us, B=10 18.4 -> 14.3 us); more cloud pairs: one CTA per cloud walks the contributors only
   // once (B=50 18.4 vs 27.5 us split, B=512 82 vs 184 us).
@@ -557,6 +600,20 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
     }
     const int per = (lmax + parts - 1) / parts;
     a.nparts = parts;
+    // early start behind the forward search that wrote these index arrays on this stream (ga_common.cuh)
+    a.ticket = nullptr;
+    a.call_id = 0;
+    a.expected = 0;
+    {
+      const LastForward& lf = last_forward();
+      if (g_pdl && lf.call_id != 0 && lf.stream == st && lf.idx1 == idx1 && lf.idx2 == idx2 && lf.b == b && lf.n == n &&
+          lf.m == m) {
+        a.ticket = lf.ticket;
+        a.call_id = lf.call_id;
+        a.expected = lf.expected;
+        a.ticket_debug = g_tickets == 2;
+      }
+    }
     static std::atomic<unsigned> done2{0};
     int dev = 0;
     GA_CUDA_TRY(cudaGetDevice(&dev));
@@ -628,4 +685,21 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
   }
   GA_LAUNCH_CHECK("nn_bwd_kernel");
   return GA_OK;
+}
+
+// Forward search + gradient for upstream gradients that are already final when the call is made (a
+// Chamfer loss: d loss / d dist is a constant).  Both kernels are launched back to back by the library,
+// so nothing else can write grad_dist* between them: gradient CTAs whose batch element is complete run
+// to the end while the search is still draining its last wave, instead of parking behind the grid
+// dependency (nn_bwd2_kernel).  Same results as ga_nn_distance_fwd followed by ga_nn_distance_bwd.
+extern "C" int ga_nn_distance_fwd_bwd(int b, int n, int m, const float* xyz1, const float* xyz2,
+                                      const float* grad_dist1, const float* grad_dist2, float* dist1, int* idx1,
+                                      float* dist2, int* idx2, float* grad_xyz1, float* grad_xyz2, int mode,
+                                      ga_stream_t stream) {
+  int rc = ga_nn_distance_fwd(b, n, m, xyz1, xyz2, dist1, idx1, dist2, idx2, mode, stream);
+  if (rc != GA_OK) return rc;
+  ga::t_gd_final = 1;
+  rc = ga_nn_distance_bwd(b, n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, stream);
+  ga::t_gd_final = 0;
+  return rc;
 }

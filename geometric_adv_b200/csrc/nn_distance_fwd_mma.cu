@@ -35,7 +35,18 @@ struct MmaCfg {
 template <class Cfg, int MODE, int MINB>
 __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const FwdArgs a) {
   constexpr int THREADS = Cfg::kThreads, QT = Cfg::kQT, CH = Cfg::kCH, T = kMmaT;
-  // dependents (the gradient kernel) may be scheduled once every CTA of this grid has started
+  // Completion tickets: clear this batch element's slot BEFORE the dependents may start (a replayed CUDA
+  // graph reuses its call id: the slot still holds the previous replay's "all done").  Dependents (the
+  // gradient kernel) may be scheduled once every CTA of this grid has passed this point.
+  if (a.ticket != nullptr) {
+    if (threadIdx.x == 0) {
+      const int jpb0 = a.tiles1 + a.tiles2;
+      atomicExch(a.ticket + ticket_slot(a.call_id, (int)(blockIdx.x / jpb0)), a.call_id << 16);
+      if (a.ticket_debug) atomicMax(a.ticket + kTicketSlots + 4, global_ns());  // start of the last CTA
+      __threadfence();
+    }
+    __syncthreads();
+  }
   asm volatile("griddepcontrol.launch_dependents;");
   extern __shared__ float4 smem_f4[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
@@ -75,6 +86,23 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
   }
   mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
             rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
+  // Completion ticket of this batch element: (call id << 16 | CTAs done).  The gradient kernel, started
+  // early as a programmatic dependent, builds its inverse index map as soon as all CTAs of an element
+  // have checked in (nn_distance_bwd.cu); a slot overwritten by another call only makes it wait longer.
+  if (a.ticket != nullptr) {
+    __syncthreads();  // every warp's dist / idx rows are written
+    if (tid == 0) {
+      __threadfence();
+      unsigned long long* slot = a.ticket + ticket_slot(a.call_id, batch);
+      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(slot), assumed;
+      do {
+        assumed = old;
+        const unsigned long long next = (assumed >> 16) == a.call_id ? assumed + 1 : ((a.call_id << 16) | 1ull);
+        old = atomicCAS(slot, assumed, next);
+      } while (old != assumed);
+      if (a.ticket_debug) atomicMax(a.ticket + kTicketSlots + 3, global_ns());  // end of the last CTA
+    }
+  }
 }
 
 // ---- persistent variant: one CTA of 16 warps per SM, warps pull 64-query jobs ----------------
@@ -469,6 +497,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) mma_filter_dump_kernel(int n, i
   }
 }
 
+int g_tickets = 1;  // tuning hook (key 18): 0 = no completion tickets (the gradient kernel waits for the whole grid)
 int g_mma_cfg = 0;  // tuning hook (key 7): 0 auto (= 5); 1-5 = (warps, chunk, CTAs/SM) combinations below
 
 template <class Cfg, int MINB>
@@ -492,8 +521,28 @@ static int launch_fwd_mma_cfg(FwdArgs a, int mode, cudaStream_t st) {
       done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
     }
   }
+  // arm the completion tickets (see the end of the kernel); off for batches beyond the slot count
+  a.ticket = nullptr;
+  a.call_id = 0;
+  if (g_tickets && a.b <= kTicketSlots && a.tiles1 + a.tiles2 < 65536) {
+    a.ticket = ticket_buffer(st);
+    if (a.ticket != nullptr) a.call_id = next_call_id();
+  }
+  a.ticket_debug = g_tickets == 2;
   k<<<(unsigned)jobs, Cfg::kThreads, Cfg::kSmem, st>>>(a);
   GA_LAUNCH_CHECK("nn_fwd_mma_kernel");
+  if (a.call_id != 0) {
+    LastForward& lf = last_forward();
+    lf.stream = st;
+    lf.idx1 = a.idx1;
+    lf.idx2 = a.idx2;
+    lf.b = a.b;
+    lf.n = a.n;
+    lf.m = a.m;
+    lf.expected = a.tiles1 + a.tiles2;
+    lf.call_id = a.call_id;
+    lf.ticket = a.ticket;
+  }
   return GA_OK;
 }
 

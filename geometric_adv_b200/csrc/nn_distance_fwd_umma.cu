@@ -557,6 +557,9 @@ extern "C" int ga_debug_umma_trace(int b, int n, int m, const float* xyz1, const
   a.dist1 = dist1; a.idx1 = idx1; a.dist2 = dist2; a.idx2 = idx2;
   a.tiles1 = a.tiles2 = 0;
   a.mdist1 = a.mdist2 = nullptr;
+  a.ticket = nullptr;
+  a.call_id = 0;
+  a.ticket_debug = 0;
   a.midx1 = a.midx2 = nullptr;
   return ga::launch_fwd_umma_impl(a, GA_MODE_CPU_EXACT, ga::as_stream(stream), trace);
 }

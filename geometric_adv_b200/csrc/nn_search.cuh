@@ -23,6 +23,10 @@ struct FwdArgs {
   int* midx1;
   float* mdist2;
   int* midx2;
+  // completion tickets (nn_fwd_mma_kernel only; nullptr / 0 = off): see ga_common.cuh
+  unsigned long long* ticket;
+  unsigned long long call_id;
+  int ticket_debug;
 };
 
 template <int THREADS, int Q, int T, int CH>

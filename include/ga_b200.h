@@ -94,10 +94,23 @@ int ga_nn_distance_fwd_ws(int b, int n, int m, const float* xyz1, const float* x
  * chamfer_cuda_backward (chamfer_cuda.cpp:12, chamfer3D.cu:176-195) and
  * NnDistanceGradOp's CPU loops (tf_nndistance.cpp:122-163).  Atomic-free: every
  * output element is accumulated by one thread in exactly the CPU loop order, so
- * the result is bit-identical to the CPU reference and run-to-run reproducible. */
+ * the result is bit-identical to the CPU reference and run-to-run reproducible.
+ * Stream semantics: launched as a programmatic dependent of the preceding kernel on
+ * `stream`.  idx1 / idx2 must be the arrays the matching ga_nn_distance_fwd call wrote,
+ * unmodified: when that call was the caller's last forward launch on this stream, the
+ * kernel starts on its index rows per batch element as soon as they are final, while
+ * the rest of the search is still running; everything else (grad_dist*) is read only
+ * behind the grid dependency. */
 int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const float* xyz2, const float* grad_dist1,
                        const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1,
                        float* grad_xyz2, ga_stream_t stream);
+/* Forward + gradient in one call for upstream gradients that are final when the call is made (the
+ * Chamfer loss of src/adv_ae.py:105,120-121 has constant d loss / d dist).  Same outputs as
+ * ga_nn_distance_fwd followed by ga_nn_distance_bwd; the gradient kernel overlaps the last wave of
+ * the search.  grad_dist1 / grad_dist2 must not be written by work still pending on `stream`. */
+int ga_nn_distance_fwd_bwd(int b, int n, int m, const float* xyz1, const float* xyz2, const float* grad_dist1,
+                           const float* grad_dist2, float* dist1, int* idx1, float* dist2, int* idx2,
+                           float* grad_xyz1, float* grad_xyz2, int mode, ga_stream_t stream);
 int ga_nn_distance_bwd_host(int b, int n, int m, const float* xyz1, const float* xyz2, const float* grad_dist1,
                             const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1,
                             float* grad_xyz2);

@@ -305,6 +305,33 @@ def test_fwd_bwd_host_graph_replay(ga, chunks):
         lib.ga_set_tuning(11, 0)
 
 
+@pytest.mark.parametrize("shape", [(50, 2048, 2048), (37, 2048, 2000), (10, 2048, 2048), (3, 300, 257), (12, 1000, 4000)])
+def test_fused_device_entry_equals_separate_calls(ga, shape):
+    """ga_nn_distance_fwd_bwd: gradient CTAs start per batch element behind the search's completion tickets
+    and never park behind the grid dependency; outputs must be the bits of the two separate calls, every
+    time (repeated: the overlap is timing dependent)."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    p = ctypes.c_void_p
+    b, n, m = shape
+    a, c = cloud(70 + b, (b, n, 3)), cloud(71 + b, (b, m, 3))
+    gd1 = np.random.default_rng(b).standard_normal((b, n)).astype(np.float32)
+    gd2 = np.random.default_rng(b + 1).standard_normal((b, m)).astype(np.float32)
+    x1, x2, g1, g2 = t(a), t(c), t(gd1), t(gd2)
+    want = ga.nn_distance(x1, x2)
+    wg = ga.nn_distance_grad(x1, x2, g1, want[1], g2, want[3])
+    st = torch.cuda.current_stream().cuda_stream
+    for rep in range(6):
+        d1 = torch.full((b, n), -1.0, device=DEV); i1 = torch.full((b, n), -1, dtype=torch.int32, device=DEV)
+        d2 = torch.full((b, m), -1.0, device=DEV); i2 = torch.full((b, m), -1, dtype=torch.int32, device=DEV)
+        o1 = torch.full((b, n, 3), float("nan"), device=DEV); o2 = torch.full((b, m, 3), float("nan"), device=DEV)
+        _lib.check(lib.ga_nn_distance_fwd_bwd(b, n, m, p(x1.data_ptr()), p(x2.data_ptr()), p(g1.data_ptr()),
+                                              p(g2.data_ptr()), p(d1.data_ptr()), p(i1.data_ptr()), p(d2.data_ptr()),
+                                              p(i2.data_ptr()), p(o1.data_ptr()), p(o2.data_ptr()), 0, p(st)))
+        for got, w in zip((d1, i1, d2, i2, o1, o2), tuple(want) + tuple(wg)):
+            assert bits_equal(got.cpu().numpy(), w.cpu().numpy()), (shape, rep)
+
+
 # ------------------------------------------------------------------ backward
 def check_bwd(ga, oracle, a, b, gd1, i1, gd2, i2):
     """Both launch shapes of the gradient kernel: one CTA per cloud, and output points split over 4 CTAs."""
