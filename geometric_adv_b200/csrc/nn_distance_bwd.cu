@@ -542,7 +542,8 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
   }
 }
 
-extern int g_tickets;  // nn_distance_fwd_mma.cu
+extern int g_tickets;                    // nn_distance_fwd_mma.cu
+extern thread_local int t_want_tickets;  // nn_distance_fwd_mma.cu
 int g_pdl = 1;         // tuning hook (key 15): 0 = plain launches (no programmatic dependent launch)
 int g_bwd_kernel = 0;  // tuning hook (key 14): 0 auto (second formulation when it applies), 1 = stable counting sort
 int g_bwd_stage = 1;   // tuning hook (key 13): 0 = gather the partner cloud from global memory (no staging)
@@ -696,7 +697,9 @@ extern "C" int ga_nn_distance_fwd_bwd(int b, int n, int m, const float* xyz1, co
                                       const float* grad_dist1, const float* grad_dist2, float* dist1, int* idx1,
                                       float* dist2, int* idx2, float* grad_xyz1, float* grad_xyz2, int mode,
                                       ga_stream_t stream) {
+  ga::t_want_tickets = 1;
   int rc = ga_nn_distance_fwd(b, n, m, xyz1, xyz2, dist1, idx1, dist2, idx2, mode, stream);
+  ga::t_want_tickets = 0;
   if (rc != GA_OK) return rc;
   ga::t_gd_final = 1;
   rc = ga_nn_distance_bwd(b, n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, stream);

@@ -39,15 +39,18 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
   // graph reuses its call id: the slot still holds the previous replay's "all done").  Dependents (the
   // gradient kernel) may be scheduled once every CTA of this grid has passed this point.
   if (a.ticket != nullptr) {
+    // one thread clears the slot and then triggers for the CTA; the others go straight to work (a barrier
+    // here would put the ~1 us of the atomic and the fence in front of every CTA)
     if (threadIdx.x == 0) {
       const int jpb0 = a.tiles1 + a.tiles2;
       atomicExch(a.ticket + ticket_slot(a.call_id, (int)(blockIdx.x / jpb0)), a.call_id << 16);
       if (a.ticket_debug) atomicMax(a.ticket + kTicketSlots + 4, global_ns());  // start of the last CTA
       __threadfence();
+      asm volatile("griddepcontrol.launch_dependents;");
     }
-    __syncthreads();
+  } else {
+    asm volatile("griddepcontrol.launch_dependents;");
   }
-  asm volatile("griddepcontrol.launch_dependents;");
   extern __shared__ float4 smem_f4[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
   float4* tgt = smem_f4;
@@ -497,7 +500,8 @@ __global__ void __launch_bounds__(Cfg::kThreads) mma_filter_dump_kernel(int n, i
   }
 }
 
-int g_tickets = 1;  // tuning hook (key 18): 0 = no completion tickets (the gradient kernel waits for the whole grid)
+int g_tickets = 1;  // tuning hook (key 18): 0 = never, 1 = for ga_nn_distance_fwd_bwd only, 2 = always + debug stamps, 3 = always
+thread_local int t_want_tickets = 0;  // set by ga_nn_distance_fwd_bwd around its forward launch
 int g_mma_cfg = 0;  // tuning hook (key 7): 0 auto (= 5); 1-5 = (warps, chunk, CTAs/SM) combinations below
 
 template <class Cfg, int MINB>
@@ -524,7 +528,10 @@ static int launch_fwd_mma_cfg(FwdArgs a, int mode, cudaStream_t st) {
   // arm the completion tickets (see the end of the kernel); off for batches beyond the slot count
   a.ticket = nullptr;
   a.call_id = 0;
-  if (g_tickets && a.b <= kTicketSlots && a.tiles1 + a.tiles2 < 65536) {
+  // The check-in costs each CTA ~1 us at its end (fence + compare-and-swap before the exit: measured 58.2 ->
+  // 60.3 us at B=50), which only the one-call entry point earns back: armed there (t_want_tickets), off for a
+  // plain ga_nn_distance_fwd.
+  if ((g_tickets >= 2 || (g_tickets == 1 && t_want_tickets)) && a.b <= kTicketSlots && a.tiles1 + a.tiles2 < 65536) {
     a.ticket = ticket_buffer(st);
     if (a.ticket != nullptr) a.call_id = next_call_id();
   }
