@@ -179,7 +179,16 @@ int ga_split_by_threshold(int b, int n, const float* pc, const float* score, flo
  * FFMA lane) through *tflops.  bench.py uses it as the FP32 roofline denominator,
  * since MEASURED_PEAKS.json holds HBM and BF16 only. */
 int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
-/* Tuning hook for benchmarks: key 0 selects the forward-kernel tile variant (0 = default). */
+/* Tuning hooks for benchmarks and tests (process-wide; defaults in parentheses):
+ *    0 forward kernel: 0 auto, 1-15 fp32-filter tile shapes, 20 HMMA grid kernel, 21 persistent HMMA,
+ *      22 tcgen05/TMEM, 23 balanced persistent HMMA          1 kNN variant            2 host path (0 auto,
+ *      1 copies, 2 zero-copy)      3 host chunks (0 auto)     4 pruned-path variant    5 cluster split S (-1 auto)
+ *    6 split kernel queries/thread  7 HMMA grid config (0 = 5)  8 persistent grids' CTA count (0 = SMs)
+ *    9 gradient CTAs per cloud (-1 auto, 0 one, 1 four, 2 two)  10 host graph replay (0 auto, 1 off, 2 at once)
+ *   11 replay chunks (0 auto)      12 tcgen05 grid CTAs (0 = SMs)  13 first gradient kernel: stage partner (1)
+ *   14 gradient kernel (0 auto = atomics + list sort, 1 = stable counting sort)   15 dependent launch (1)
+ *   16 all-pairs kernel (0 auto = tensor-core scan, 1 = fp32 filter)   17 replay: dist/idx mirrored to the host
+ *      (0 auto, 1 never, 2 always)   18 completion tickets (0 never, 1 one-call entry only, 2 always + debug, 3 always) */
 int ga_set_tuning(int key, int value);
 /* Empty-kernel launch floor in microseconds (average over `reps` launches). */
 int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);
