@@ -28,7 +28,7 @@ h = torch.rand(2, 64, 3); ga.nn_distance(h, h); ga.knn_dists(h, 3)
 from geometric_adv_b200 import _lib
 import ctypes
 lib = _lib.load()
-for v in (20, 21, 22):
+for v in (20, 21, 22, 23):
     lib.ga_set_tuning(0, v)
     for (b, n, m) in [(2, 300, 517), (3, 2048, 2048)]:
         ga.nn_distance(cl(b, n), cl(b, m))
@@ -46,4 +46,17 @@ hb = [torch.rand(b, n, 3).pin_memory() - 0.5, torch.rand(b, n, 3).pin_memory() -
       torch.empty(b, n, 3).pin_memory(), torch.empty(b, n, 3).pin_memory()]
 for _ in range(3):
     _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, n, *[ctypes.c_void_p(x.data_ptr()) for x in hb], 0))
+# one-call forward + gradient (completion tickets, early gradient CTAs), tensor-core all-pairs
+b, n = 20, 2048
+xa, xb = cl(b, n), cl(b, n)
+ga1 = torch.rand(b, n, device=dev); ga2 = torch.rand(b, n, device=dev)
+od1 = torch.empty(b, n, device=dev); oi1 = torch.empty(b, n, dtype=torch.int32, device=dev)
+od2 = torch.empty(b, n, device=dev); oi2 = torch.empty(b, n, dtype=torch.int32, device=dev)
+og1 = torch.empty(b, n, 3, device=dev); og2 = torch.empty(b, n, 3, device=dev)
+P = ctypes.c_void_p
+for _ in range(2):
+    _lib.check(lib.ga_nn_distance_fwd_bwd(b, n, n, P(xa.data_ptr()), P(xb.data_ptr()), P(ga1.data_ptr()), P(ga2.data_ptr()),
+                                          P(od1.data_ptr()), P(oi1.data_ptr()), P(od2.data_ptr()), P(oi2.data_ptr()),
+                                          P(og1.data_ptr()), P(og2.data_ptr()), 0, P(torch.cuda.current_stream().cuda_stream)))
+ga.chamfer_all_pairs(cl(6, 512))
 torch.cuda.synchronize(); print("driver ok")
