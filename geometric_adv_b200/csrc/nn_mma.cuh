@@ -271,6 +271,28 @@ __device__ __forceinline__ unsigned tile_candidate_mask(const float4* __restrict
   return __funnelshift_l(m, m, 2 * rot);  // walk position i holds pair (i + rot) mod 16
 }
 
+// Two tiles for two queries in one walk: twice the independent loads and FMAs in flight (a lane's two
+// queries are otherwise served one after the other, each a chain of LDS -> FFMA2 -> compare).
+__device__ __forceinline__ void tile_candidate_mask2(const float4* __restrict__ tpa, const float4* __restrict__ tpb,
+                                                     const float (&ax2)[2], const float (&ay2)[2],
+                                                     const float (&az2)[2], const float (&thr)[2], unsigned& ma,
+                                                     unsigned& mb) {
+  constexpr int T = kMmaT;
+  const int rot = threadIdx.x & (T / 2 - 1);
+  ma = 0;
+  mb = 0;
+#pragma unroll
+  for (int i = 0; i < T / 2; i++) {
+    const int pp = (i + rot) & (T / 2 - 1);
+    const float2 fa = filter_pair(tpa[2 * pp], tpa[2 * pp + 1], ax2[0], ay2[0], az2[0]);
+    const float2 fb = filter_pair(tpb[2 * pp], tpb[2 * pp + 1], ax2[1], ay2[1], az2[1]);
+    ma |= (!(fa.x > thr[0]) ? (1u << (2 * i)) : 0u) | (!(fa.y > thr[0]) ? (2u << (2 * i)) : 0u);
+    mb |= (!(fb.x > thr[1]) ? (1u << (2 * i)) : 0u) | (!(fb.y > thr[1]) ? (2u << (2 * i)) : 0u);
+  }
+  ma = __funnelshift_l(ma, ma, 2 * rot);
+  mb = __funnelshift_l(mb, mb, 2 * rot);
+}
+
 // Refine for the tensor-core scan.  Per query: cnt qualifying tiles (ta, tb valid for cnt <= 2).
 //  1. first tile, one lane per query: fp32 filter -> candidate mask -> one or two exact evaluations
 //     (all lanes in step); more than two candidates -> exact warp scan of the chunk;
@@ -284,18 +306,31 @@ __device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __r
   constexpr int T = kMmaT;
   const int lane = threadIdx.x & 31;
   bool hard[Q], second[Q];
+  unsigned masks[Q];
+  int g0s[Q];
+  bool use[Q];
 #pragma unroll
   for (int j = 0; j < Q; j++) {
     hard[j] = s.valid[j] && cnt[j] > 2;
     second[j] = s.valid[j] && cnt[j] == 2;
-    unsigned mask = 0;
-    int g0 = 0;
-    if (s.valid[j] && cnt[j] >= 1 && cnt[j] <= 2) {
-      g0 = c0 + ta[j] * T;
-      const int rem = nt - g0;  // >= 1: only staged tiles are listed
-      mask = tile_candidate_mask(tgt + (size_t)ta[j] * T, s.ax2[j], s.ay2[j], s.az2[j], thr[j]);
-      mask &= rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-    }
+    use[j] = s.valid[j] && cnt[j] >= 1 && cnt[j] <= 2;
+    g0s[j] = c0 + (use[j] ? ta[j] : 0) * T;  // an unused slot walks tile 0 and drops the mask
+    masks[j] = 0;
+  }
+  if constexpr (Q == 2) {
+    tile_candidate_mask2(tgt + (size_t)(g0s[0] - c0), tgt + (size_t)(g0s[1] - c0), s.ax2, s.ay2, s.az2, thr, masks[0],
+                         masks[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < Q; j++)
+      masks[j] = tile_candidate_mask(tgt + (size_t)(g0s[j] - c0), s.ax2[j], s.ay2[j], s.az2[j], thr[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    const int g0 = g0s[j];
+    const int rem = nt - g0;  // >= 1: only staged tiles are listed (and tile 0 exists)
+    unsigned mask = use[j] ? masks[j] : 0u;
+    mask &= rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
     const int n = __popc(mask);
     if (n >= 1 && n <= 2)
       eval_candidate<MODE>(tgt, c0, g0 + __ffs(mask) - 1, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
