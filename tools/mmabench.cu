@@ -24,6 +24,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(z[0]), "f"(z[1]), "f"(z[2]), "f"(z[3]));
 }
+__device__ __forceinline__ void mma16816_inplace(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float d;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -37,6 +42,8 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // MODE 4: as 1 with the zero C operand in a REAL register quad (opaque to the compiler) instead of RZ
 // MODE 5: as 2 (no FMNMX3) with the real-register zero C
 // MODE 6: chained accumulators + LDS (c += a*b, B from shared memory)
+// MODE 7: as 1, but the accumulator quad is zeroed in place and the MMA accumulates into it (C == D) -- ptxas
+//         folds the zero back into the RZ form (checked in SASS), so this measures the same loop as mode 1
 template <int MODE, int MT>
 __global__ void __launch_bounds__(512) bench(float* out, int steps, long long* cyc, float rzero) {
   __shared__ uint2 bfrag[64 * 32];
@@ -67,10 +74,15 @@ __global__ void __launch_bounds__(512) bench(float* out, int steps, long long* c
   uint2 bf = bfrag[lane];
 #pragma unroll 4
   for (int s = 0; s < steps; s++) {
-    if (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 6) bf = bfrag[(s & 63) * 32 + lane];
+    if (MODE == 1 || MODE == 2 || MODE == 4 || MODE == 5 || MODE == 6 || MODE == 7) bf = bfrag[(s & 63) * 32 + lane];
 #pragma unroll
     for (int i = 0; i < MT; i++) {
-      if (MODE == 0 || MODE == 6) {
+      if (MODE == 7) {
+        c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+        mma16816_inplace(c[i], a[i], bf.x, bf.y);
+        rm[i][0] = fmin3(rm[i][0], c[i][0], c[i][1]);
+        rm[i][1] = fmin3(rm[i][1], c[i][2], c[i][3]);
+      } else if (MODE == 0 || MODE == 6) {
         mma16816(c[i], a[i], bf.x, bf.y, c[i]);
       } else {
         mma16816(c[i], a[i], bf.x, bf.y, z);
@@ -139,6 +151,7 @@ int main() {
   for (int w : {4, 8, 16}) run<2, 4>("hmma zeroC + lds", w, sms);
   for (int w : {4, 8, 16}) run<3, 4>("hmma zeroC + 2 fmnmx3 (regs)", w, sms);
   for (int w : {8, 16}) run<6, 4>("hmma chained + lds", w, sms);
+  for (int w : {8, 16}) run<7, 4>("hmma zeroed-in-place + lds + 2 fmnmx3", w, sms);
   for (int w : {8, 16}) run<5, 4>("hmma regzeroC + lds", w, sms);
   for (int w : {8, 16}) run<4, 4>("hmma regzeroC + lds + 2 fmnmx3", w, sms);
   for (int w : {4, 8, 12, 16}) run<1, 4>("hmma zeroC + lds + 2 fmnmx3", w, sms);
