@@ -9,8 +9,12 @@
 // of source clouds through it (all clouds stay L2-resident: 2,000 x 24 KB = 49 MB);
 // no per-point dist/idx array is ever written.  CD[i,j] = D[j->i] + D[i->j].
 // Same filter-and-refine search as nn_distance_fwd.cu, so every per-point distance
-// is bit-identical to the reference arithmetic; the per-cloud mean uses a fixed
-// summation tree (the reference's reduce_mean order is unpinned: tolerance 1e-6).
+// is bit-identical to the reference arithmetic; the per-cloud mean uses ONE fixed
+// summation order in every kernel of the library (cloud_mean_sum below = the order of
+// chamfer_per_cloud_kernel, reduce.cu), so the matrix is bit-identical whichever kernel,
+// block size or row split produced it, and bit-identical to
+// ga_chamfer_per_cloud(ga_nn_distance_fwd(...)).  (The reference's own reduce_mean order
+// is unpinned: tolerance 1e-6 against the oracle.)
 #include <atomic>
 
 #include "nn_mma.cuh"
@@ -30,6 +34,33 @@ struct PairArgs {
 
 using PairCfg = FwdCfg<128, 4, 32, 2048>;
 
+// Canonical sum of the n per-point distances d[] (shared memory) of one cloud: 256 virtual
+// threads v each add the slice d[v], d[v+256], ... in ascending order, each virtual warp folds its
+// 32 slices with an xor-shuffle tree, and the 8 warp sums are added in ascending order -- exactly
+// chamfer_per_cloud_kernel (reduce.cu).  Call with all THREADS (128 or 256) threads of the CTA,
+// after a barrier that makes d[] visible; `red` holds 8 floats.  The result is valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ float cloud_mean_sum(const float* __restrict__ d, int n, float* __restrict__ red, int tid) {
+  static_assert(THREADS == 128 || THREADS == 256, "virtual thread mapping");
+  constexpr int V = 256 / THREADS;  // virtual threads per thread: v = tid + u * THREADS (warp w + u * THREADS / 32)
+  float s[V];
+#pragma unroll
+  for (int u = 0; u < V; u++) {
+    s[u] = 0.0f;
+    for (int j = tid + u * THREADS; j < n; j += 256) s[u] += d[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    if ((tid & 31) == 0) red[(tid >> 5) + u * (THREADS / 32)] = s[u];
+  }
+  __syncthreads();
+  float t = 0.0f;
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += red[w];
+  }
+  return t;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(PairCfg::kThreads) all_pairs_directed_kernel(const PairArgs a) {
   using Cfg = PairCfg;
@@ -37,7 +68,8 @@ __global__ void __launch_bounds__(PairCfg::kThreads) all_pairs_directed_kernel(c
   extern __shared__ float4 smem_f4[];
   float4* tgt = smem_f4;
   float* red = reinterpret_cast<float*>(smem_f4 + CH + 2 * kPipeU);  // [32]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* dpt = red + 32;                                               // [CH] per-point distances of one source cloud
+  const int tid = threadIdx.x;
   const int n = a.n;
   const int nblk = (a.na + a.ablk - 1) / a.ablk;
   const int bj = blockIdx.x / nblk;            // target cloud (slow index: neighbours share sources in L2)
@@ -50,7 +82,7 @@ __global__ void __launch_bounds__(PairCfg::kThreads) all_pairs_directed_kernel(c
   const int a_end = min(a.na, (ab + 1) * a.ablk);
   for (int ai = ab * a.ablk; ai < a_end; ai++) {
     const float* qpts = a.clouds + (size_t)(a.a0 + ai) * n * 3;
-    float part = 0.0f;  // this thread's distances, summed in (tile, slot) order
+    __syncthreads();  // dpt[] / red[] free (staging / previous cloud done)
     for (int qt = 0; qt < qtiles; qt++) {
       QueryState<Q> s;
       load_queries<Cfg, MODE>(s, qpts, n, qt, tpts, tid);
@@ -61,19 +93,12 @@ __global__ void __launch_bounds__(PairCfg::kThreads) all_pairs_directed_kernel(c
         float d;
         int i;
         finish_query<Q>(s, j, d, i);
-        part += d;
+        dpt[qt * QT + j * THREADS + tid] = d;
       }
     }
-    // fixed tree: lanes by xor-shuffle, then warps in order
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __syncthreads();  // red[] free (staging / previous cloud done)
-    if (lane == 0) red[warp] = part;
     __syncthreads();
+    const float t = cloud_mean_sum<THREADS>(dpt, n, red, tid);
     if (tid == 0) {
-      float t = 0.0f;
-#pragma unroll
-      for (int w = 0; w < THREADS / 32; w++) t += red[w];
       float* o = a.out + (long long)ai * a.stride_a + (long long)bj * a.stride_b;
       const float v = t / (float)n;
       *o = a.accumulate ? *o + v : v;
@@ -93,14 +118,15 @@ constexpr size_t kPairMmaOffRed = (size_t)kPairMmaCH * 16 + (size_t)kPipeU * 32;
 constexpr size_t kPairMmaOffB = kPairMmaOffRed + 32 * 4;
 constexpr size_t kPairMmaOffCnt = kPairMmaOffB + (size_t)kPairMmaCH * 32;
 constexpr size_t kPairMmaOffTile = kPairMmaOffCnt + (size_t)kPairMmaWarps * kMmaQW * 4;
-constexpr size_t kPairMmaSmem = kPairMmaOffTile + (size_t)kPairMmaWarps * kMmaQW * 4;
+constexpr size_t kPairMmaOffDpt = kPairMmaOffTile + (size_t)kPairMmaWarps * kMmaQW * 4;
+constexpr size_t kPairMmaSmem = kPairMmaOffDpt + (size_t)kPairMmaCH * 4;
 
-// One 64-query job: returns the sum of this lane's (up to two) exact distances.  Not inlined: inside
+// One 64-query job: stores this lane's (up to two) exact distances in dpt[].  Not inlined: inside
 // the caller's loops ptxas serialises the HMMAs of the scan on one accumulator quad (see persist_job).
 template <int MODE>
-__device__ __noinline__ float pair_job(const float* __restrict__ qpts, const float* __restrict__ tpts, int n, int qbase,
-                                       const float4* __restrict__ tgt, const uint4* __restrict__ bfrag, float bm,
-                                       int* wcnt, unsigned short* wtile) {
+__device__ __noinline__ void pair_job(const float* __restrict__ qpts, const float* __restrict__ tpts, int n, int qbase,
+                                      const float4* __restrict__ tgt, const uint4* __restrict__ bfrag, float bm,
+                                      int* wcnt, unsigned short* wtile, float* __restrict__ dpt) {
   const int lane = threadIdx.x & 31;
   MmaRows R;
   mma_load_rows(R, qpts, n, qbase, lane);
@@ -110,16 +136,14 @@ __device__ __noinline__ float pair_job(const float* __restrict__ qpts, const flo
 #pragma unroll
   for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
   mma_chunk<MODE>(R, s, mrun, tgt, bfrag, 0, n, n, bm, wcnt, wtile, lane);
-  float part = 0.0f;
 #pragma unroll
   for (int j = 0; j < 2; j++) {
     if (!s.valid[j]) continue;
     float d;
     int i;
     finish_query<2>(s, j, d, i);
-    part += d;
+    dpt[qbase + 16 * (lane & 3) + (lane >> 2) + 8 * j] = d;  // the lane's queries: see mma_init_queries
   }
-  return part;
 }
 
 template <int MODE>
@@ -130,7 +154,8 @@ __global__ void __launch_bounds__(kPairMmaWarps * 32, 2) all_pairs_directed_mma_
   float4* tgt = smem_f4;
   float* red = reinterpret_cast<float*>(smem + kPairMmaOffRed);
   uint4* bfrag = reinterpret_cast<uint4*>(smem + kPairMmaOffB);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* dpt = reinterpret_cast<float*>(smem + kPairMmaOffDpt);
+  const int tid = threadIdx.x, warp = tid >> 5;
   int* wcnt = reinterpret_cast<int*>(smem + kPairMmaOffCnt) + warp * kMmaQW;
   unsigned short* wtile = reinterpret_cast<unsigned short*>(smem + kPairMmaOffTile) + warp * kMmaQW * 2;
   const int n = a.n;
@@ -145,19 +170,12 @@ __global__ void __launch_bounds__(kPairMmaWarps * 32, 2) all_pairs_directed_mma_
   const int a_end = min(a.na, (ab + 1) * a.ablk);
   for (int ai = ab * a.ablk; ai < a_end; ai++) {
     const float* qpts = a.clouds + (size_t)(a.a0 + ai) * n * 3;
-    float part = 0.0f;
+    __syncthreads();  // dpt[] / red[] free (previous cloud done)
     for (int job = warp; job < jobs; job += kPairMmaWarps)
-      part += pair_job<MODE>(qpts, tpts, n, job * kMmaQW, tgt, bfrag, bm, wcnt, wtile);
-    // fixed tree: lanes by xor-shuffle, then warps in order
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __syncthreads();  // red[] free (staging / previous cloud done)
-    if (lane == 0) red[warp] = part;
+      pair_job<MODE>(qpts, tpts, n, job * kMmaQW, tgt, bfrag, bm, wcnt, wtile, dpt);
     __syncthreads();
+    const float t = cloud_mean_sum<THREADS>(dpt, n, red, tid);
     if (tid == 0) {
-      float t = 0.0f;
-#pragma unroll
-      for (int w = 0; w < kPairMmaWarps; w++) t += red[w];
       float* o = a.out + (long long)ai * a.stride_a + (long long)bj * a.stride_b;
       const float v = t / (float)n;
       *o = a.accumulate ? *o + v : v;
@@ -166,6 +184,7 @@ __global__ void __launch_bounds__(kPairMmaWarps * 32, 2) all_pairs_directed_mma_
 }
 
 int g_pairs_kernel = 0;  // tuning hook (key 16): 0 auto (tensor-core scan from 256 points), 1 = fp32 filter scan
+int g_pairs_ablk = 0;    // tuning hook (key 19): source clouds per CTA, 0 = auto (choose_ablk)
 
 static int launch_directed(const PairArgs& a, int mode, cudaStream_t st) {
   if (a.na <= 0 || a.nb <= 0) return GA_OK;
@@ -190,13 +209,15 @@ static int launch_directed(const PairArgs& a, int mode, cudaStream_t st) {
   }
   auto k = mode == GA_MODE_CPU_EXACT ? all_pairs_directed_kernel<GA_MODE_CPU_EXACT>
                                      : all_pairs_directed_kernel<GA_MODE_GPU_REF>;
-  GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::kSmem));
-  k<<<(unsigned)ctas, PairCfg::kThreads, PairCfg::kSmem, st>>>(a);
+  constexpr size_t kPairSmem = PairCfg::kSmem + (size_t)PairCfg::kCH * 4;  // + dpt[]
+  GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
+  k<<<(unsigned)ctas, PairCfg::kThreads, kPairSmem, st>>>(a);
   GA_LAUNCH_CHECK("all_pairs_directed_kernel");
   return GA_OK;
 }
 
 static int choose_ablk(int na, int nb) {
+  if (g_pairs_ablk > 0) return g_pairs_ablk;
   // enough CTAs to fill the machine several times over, as much reuse of the staged cloud as that allows
   const long long want = (long long)sm_count() * 16;
   int ablk = 16;

@@ -128,7 +128,7 @@ def save_chamfer_nn_files(data_path, chamfer_dist_mat, slice_idx, file_name_part
     dm = chamfer_dist_mat.detach().cpu().numpy() if isinstance(chamfer_dist_mat, torch.Tensor) else np.asarray(
         chamfer_dist_mat)
     dm = dm.astype(np.float32)
-    assert dm.min() >= 0, "the chamfer_dist_mat matrix was not filled correctly"
+    assert np.isfinite(dm).all() and dm.min() >= 0, "the chamfer_dist_mat matrix was not filled correctly"
     tail = "_".join(file_name_parts)
     p1 = os.path.join(data_path, "chamfer_dist_mat_complete_" + tail + ".npy")
     p2 = os.path.join(data_path, "chamfer_nn_idx_complete_" + tail + ".npy")

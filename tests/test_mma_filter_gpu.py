@@ -139,3 +139,98 @@ def test_full_size_equals_plain_kernel(ga):
         got = run_variant(ga, lib, a, b, cfg)
         for g, w in zip(got, want):
             assert bits_equal(g, w), "cfg %d" % cfg
+
+
+# ---- adversarial search for the filter bound ------------------------------------
+def _force_low_bits(v, pattern, nbits):
+    """Replace the low `nbits` mantissa bits of every fp32 in v by `pattern` (bf16-split residual extremes)."""
+    i = v.astype(np.float32).view(np.uint32)
+    mask = np.uint32((1 << nbits) - 1)
+    return ((i & ~mask) | (np.uint32(pattern) & mask)).view(np.float32)
+
+
+def _adversarial_families(rng, n, m):
+    """(name, queries, targets): inputs built to maximise |h - g| / (u s^2).
+    The dropped terms Q1 t3 + Q3 t1 are largest when the third bf16 piece of every coordinate is at its
+    extreme (low mantissa bits 0x7f/0x80/0xff after two bf16 roundings) and |q_c| = A, |t_c| = Bm on all
+    three axes; the accumulation error is largest when the 15 products have the same sign and the
+    largest exponent spread; the norm rounding when |t|^2 sits just below a power of two."""
+    fams = []
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32)
+    for pat, nb in [(0xFF, 8), (0x7F, 8), (0x80, 8), (0x81, 8), (0xFFFF, 16), (0x7FFF, 16), (0x8000, 16),
+                    (0x807F, 16), (0x7F80, 16), (0xFF7F, 16), (0x80FF, 16)]:
+        for lo in (0.5, 0.75, 0.99):
+            q = (rng.uniform(lo, 1.0, (n, 3)).astype(np.float32) * corners[rng.integers(0, 8, n)])
+            t_ = (rng.uniform(lo, 1.0, (m, 3)).astype(np.float32) * corners[rng.integers(0, 8, m)])
+            fams.append(("bits%x/%d lo%.2f" % (pat, nb, lo), _force_low_bits(q, pat, nb), _force_low_bits(t_, pat, nb)))
+    # same-sign products (q = -t direction: every term of -2 q.t and |t|^2 positive), and the cancelling case
+    base = rng.uniform(0.5, 1.0, (m, 3)).astype(np.float32)
+    fams.append(("all-positive terms", -base[:n] * np.float32(0.999), base))
+    fams.append(("cancelling q=t/2", (base[:n] * np.float32(0.5)), base))
+    fams.append(("cancelling q=t", base[:n].copy(), base))
+    # mixed magnitudes: one axis dominant, others tiny (exponent spread inside the accumulation)
+    mix_q = rng.uniform(-1, 1, (n, 3)).astype(np.float32) * np.array([1.0, 2.0 ** -9, 2.0 ** -17], np.float32)
+    mix_t = rng.uniform(-1, 1, (m, 3)).astype(np.float32) * np.array([2.0 ** -17, 1.0, 2.0 ** -9], np.float32)
+    fams.append(("mixed magnitudes", mix_q, mix_t))
+    # |t|^2 just below / above powers of two, coordinates just below powers of two
+    near2 = np.nextafter(np.float32(1.0), np.float32(0.0)) * np.ones((m, 3), np.float32) * corners[rng.integers(0, 8, m)]
+    fams.append(("just below 1", near2[:n] * np.float32(-1), near2))
+    sq = np.float32(np.sqrt(1.0 / 3.0))
+    fams.append(("norm near 1", rng.uniform(-1, 1, (n, 3)).astype(np.float32),
+                 (np.full((m, 3), sq, np.float32) * corners[rng.integers(0, 8, m)])))
+    # adversarial-attack regime: the two clouds nearly coincide, plus an offset from the origin
+    cl = rng.uniform(-0.5, 0.5, (m, 3)).astype(np.float32)
+    fams.append(("near-duplicate", cl[:n] + rng.normal(0, 1e-4, (n, 3)).astype(np.float32), cl))
+    fams.append(("offset 3", cl[:n] + np.float32(3.0), cl + np.float32(3.0)))
+    return fams
+
+
+def test_filter_bound_adversarial_search(ga, oracle):
+    """Directed search over inputs that stress each term of the bound in nn_mma.cuh; the measured worst case
+    must stay below e2 = 330 u s^2, and the whole kernel must still return the reference's bits on them."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1234)
+    n, m = 256, 2048
+    worst = (0.0, None)
+    for name, q, tg in _adversarial_families(rng, n, m):
+        q = np.ascontiguousarray(q, np.float32)
+        tg = np.ascontiguousarray(tg, np.float32)
+        h = mma_filter(lib, q, tg).astype(np.float64)
+        q64, t64 = q.astype(np.float64), tg.astype(np.float64)
+        g = (t64 * t64).sum(1)[None, :] - 2.0 * q64 @ t64.T
+        s = float(np.abs(q).max() + np.abs(tg).max())
+        err = float(np.abs(h - g).max() / (U * s * s))
+        if err > worst[0]:
+            worst = (err, name)
+        assert err <= 330.0, "%s: |h-g| = %.1f u s^2 exceeds the documented bound" % (name, err)
+        check(ga, oracle, q[None], tg[None], cfgs=[4, 5])
+    print("adversarial worst case: %.1f u s^2 (%s), bound 330" % worst)
+    # the worst case of the round-2 search is committed in tests/golden/mma_filter_worst.json; a larger value
+    # here means the search found something new -- still within the bound, but worth recording
+    import json
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "mma_filter_worst.json"), "w") as f:
+        json.dump({"err_u_s2": worst[0], "family": worst[1], "bound": 330.0}, f)
+
+
+def test_filter_bound_hypothesis(ga):
+    """Random search (hypothesis): scales, offsets and bit patterns drawn freely; bound must hold."""
+    from hypothesis import given, settings, strategies as st
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(seed=st.integers(0, 2 ** 31 - 1), eq=st.integers(-20, 20), et=st.integers(-20, 20),
+           pat=st.integers(0, 0xFFFF), off=st.floats(-2.0, 2.0))
+    def run(seed, eq, et, pat, off):
+        rng = np.random.default_rng(seed)
+        q = _force_low_bits(rng.uniform(-1, 1, (64, 3)).astype(np.float32) * np.float32(2.0 ** eq) + np.float32(off * 2.0 ** eq), pat, 16)
+        tg = _force_low_bits(rng.uniform(-1, 1, (512, 3)).astype(np.float32) * np.float32(2.0 ** et) + np.float32(off * 2.0 ** et), pat >> 3, 16)
+        h = mma_filter(lib, q, tg).astype(np.float64)
+        g = (tg.astype(np.float64) ** 2).sum(1)[None, :] - 2.0 * q.astype(np.float64) @ tg.astype(np.float64).T
+        s = float(np.abs(q).max() + np.abs(tg).max())
+        assert np.abs(h - g).max() <= 330.0 * U * s * s
+
+    run()

@@ -22,9 +22,12 @@ for (S, rows, n) in [(512, 128, 2048), (2000, 250, 2048), (512, 128, 1000)]:
         ms = e0.elapsed_time(e1)
         res[name] = {"ms": ms, "evals_per_s": rows * S * float(n) * n / (ms * 1e-3)}
         mats[name] = o.clone()
+        assert bool(torch.isfinite(o).all()), "non-finite all-pairs output (%s, S=%d)" % (name, S)
     lib.ga_set_tuning(16, 0)
     ok = mats["fp32"] > 0  # the diagonal (a cloud against itself) is exactly 0 in both
     res["max_rel_diff_between_kernels"] = float(((mats["mma"] - mats["fp32"]).abs()[ok] / mats["fp32"][ok]).max())
+    res["nonpositive_entries"] = int((~ok).sum())
+    print("torch", torch.__version__, "ok count", int(ok.sum()), "of", ok.numel())
     out["S%d_rows%d_n%d" % (S, rows, n)] = res
     print(S, rows, n, res, flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
