@@ -317,15 +317,35 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_blocks.append((time.perf_counter() - t0) / K * 1e3)  # ms, wall clock: results are on the host
         time.sleep(0.05)
-    t_e2e = min(e2e_blocks)
+    t_e2e = float(np.median(e2e_blocks))
+    t_e2e_min = min(e2e_blocks)
+
+    # the attack consumes only the gradients on the host (and a per-cloud loss): dist / idx stay on the device
+    def e2e_attack_step():
+        _lib.check(lib.ga_nn_distance_fwd_bwd_host(
+            B, N, M, p(hx1.data_ptr()), p(hx2.data_ptr()), p(hg1.data_ptr()), p(hg2.data_ptr()),
+            None, None, None, None, p(ho1.data_ptr()), p(ho2.data_ptr()), 0))
+
+    for _ in range(3):
+        e2e_attack_step()
+    atk_blocks = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        for _ in range(K):
+            e2e_attack_step()
+        torch.cuda.synchronize()
+        atk_blocks.append((time.perf_counter() - t0) / K * 1e3)
+        time.sleep(0.05)
+    t_e2e_atk = float(np.median(atk_blocks))
     h2d = (B * N * 3 + B * M * 3 + B * N + B * M) * 4
     d2h = (2 * B * N + 2 * B * M + B * N * 3 + B * M * 3) * 4
 
     # ---- max over ranks --------------------------------------------------------------------
-    times = torch.tensor([t_step, t_fwd, t_bwd, t_e2e, t_sustained, t_fused], dtype=torch.float64, device=dev)
+    times = torch.tensor([t_step, t_fwd, t_bwd, t_e2e, t_sustained, t_fused, t_e2e_min, t_e2e_atk], dtype=torch.float64,
+                         device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_step, t_fwd, t_bwd, t_e2e, t_sustained, t_fused = [float(x) for x in times.tolist()]
+    t_step, t_fwd, t_bwd, t_e2e, t_sustained, t_fused, t_e2e_min, t_e2e_atk = [float(x) for x in times.tolist()]
 
     # ---- the caller of the hot path: attack iterations per second (BASELINE metric, second half) ----
     attack = None
@@ -341,6 +361,14 @@ def run_ours(args):
                                       "pairs_per_step_all_gpus": ab * world}
         attack["what"] = ("one step = everything src/adv_ae.py:217-246 does once (update + metric re-evaluation + "
                           "best-so-far), random-init PointNet AE, CUDA-graph replay; pairs sharded over GPUs")
+
+    legs = None
+    if not args.no_legs:
+        legs = {}
+        legs["all_pairs"] = leg_all_pairs(dev, world, rank, fp32_peak, args.quick)
+        legs["knn"] = leg_knn(dev, world, rank, fp32_peak, flush, args.quick)
+        if not args.no_attack:
+            legs["attack_250_pairs"] = leg_attack(dev, world, rank, args.quick)
 
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -380,12 +408,18 @@ def run_ours(args):
             "e2e": {"value": pairs / (t_e2e * 1e-3), "unit": UNIT, "ms_per_step": t_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "ga_nn_distance_fwd_bwd_host (C ABI, pinned host buffers)",
-                    "timing": "best of 5 blocks of K steps (wall clock); blocks_ms lists every block of rank 0",
-                    "blocks_ms": e2e_blocks},
+                    "timing": "MEDIAN of 5 blocks of K steps (wall clock, max over ranks); blocks_ms lists every block "
+                              "of rank 0; min_ms_per_step is the best block",
+                    "min_ms_per_step": t_e2e_min, "blocks_ms": e2e_blocks,
+                    "attack_shaped": {"value": pairs / (t_e2e_atk * 1e-3), "ms_per_step": t_e2e_atk,
+                                      "d2h_bytes_per_step": (B * N * 3 + B * M * 3) * 4,
+                                      "what": "same call with dist/idx = NULL: only the gradients return to the host"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": fwd_kernel, "achieved": achieved, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
+                         "traffic_source": "static: dram__bytes_read+write of one ncu --set full capture of this kernel at "
+                                           "this shape (profiles/traffic.json), not measured in this run",
                          "flop_per_point_pair": FLOP_PER_PAIR, "ms_per_launch": t_fwd,
                          "peak_source": "ga_probe_fp32_peak (FFMA loop, measured on this device; "
                                         "MEASURED_PEAKS.json has no FP32 entry)",
@@ -396,6 +430,7 @@ def run_ours(args):
                           "bwd_algorithmic_GBps": 32.0 * B * (N + M) / (t_bwd * 1e-3) / 1e9,
                           "wall_s_timed_region": wall},
             "attack": attack,
+            "legs": legs,
             "cpu_baseline": {"value": B * N * M / cpu_t, "unit": UNIT, "cores": cpu_threads, "kind": kind,
                              "sample": "%d fwd+bwd passes over all %d cloud pairs (%.1f s of wall clock on %d threads)"
                                        % (cpu_passes, B, cpu_t * cpu_passes, cpu_threads),
@@ -408,13 +443,180 @@ def run_ours(args):
     return 0
 
 
+
+# ----------------------------------------------------------------------------- legs: configs 3 / 4 / 5
+# Strong scaling: the TOTAL work of each leg is fixed (BASELINE.json configs[2..4]) and sharded over the ranks;
+# every time below is CUDA-event time on the launching stream, max over ranks.
+AP_S, AP_CLASSES, AP_TOPK = 2000, 13, 5
+KNN_B, KNN_K = 500, 10
+ATK_SOURCES, ATK_TARGETS, ATK_ITERS, ATK_THRESH = 25, 10, 500, 400
+
+
+def _max_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def leg_all_pairs(dev, world, rank, fp32_peak, quick):
+    """configs[3]: prepare_indices all-pairs Chamfer over 2,000 synthetic 2048-point shapes (4M cloud pairs),
+    row blocks per rank, ONE all-gather of the directed blocks, per-class argsort of the rows on the GPU,
+    all-gather of the finished rows (attacker/prepare_indices_for_attack.py:104-180)."""
+    import torch
+    from geometric_adv_b200 import sharding
+    s = 256 if quick else AP_S
+    g = torch.Generator().manual_seed(3)
+    clouds = (torch.rand(s, N, 3, generator=g) - 0.5).to(dev)
+    slice_idx = [int(round(i * s / AP_CLASSES)) for i in range(AP_CLASSES + 1)]
+    warm = clouds[: max(world * 8, 64)].contiguous()
+    sharding.prepare_indices(warm, [0, warm.shape[0]])           # page in kernels / NCCL channels
+    torch.cuda.synchronize()
+    runs = []
+    for _ in range(2):
+        tm = {}
+        cd, nn = sharding.prepare_indices(clouds, slice_idx, timings=tm)
+        runs.append(tm)
+    best = min(runs, key=lambda t: t["total_ms"])
+    keys = ["directed_ms", "gather_directed_ms", "symmetrize_sort_ms", "gather_results_ms", "total_ms"]
+    directed, gather1, sortms, gather2, total = _max_over_ranks([best[k] for k in keys], dev, world)
+    top = sharding.nearest_targets_gpu(nn, slice_idx, AP_TOPK)
+    lo, hi = sharding.shard_range(s, world, rank)
+    out = {
+        "workload": "configs[3]: all-pairs Chamfer, %d shapes x %d points (%d cloud pairs), row blocks over %d GPU(s), "
+                    "%d classes, top-%d targets per class" % (s, N, s * s, world, AP_CLASSES, AP_TOPK),
+        "scaling": "strong", "seconds": total * 1e-3, "cloud_pairs_per_s": s * s / (total * 1e-3),
+        "point_pairs_per_s": 0.5 * s * s * float(N) * N / (total * 1e-3),
+        "phases_ms": {"directed_kernel": directed, "all_gather_directed": gather1, "symmetrize_sort": sortms,
+                      "all_gather_results": gather2},
+        "gather_share": (gather1 + gather2) / total,
+        "checks": {"symmetric": bool(torch.equal(cd, cd.t())), "zero_diagonal": not bool(cd.diagonal().any()),
+                   "finite": bool(torch.isfinite(cd).all()), "top_shape": list(top.shape)},
+        # 8 FLOP per point pair, one squared distance serving both directions: this rank's rows x S x N^2 / 2
+        "roofline": {"bound": "fp32", "kernel": "all_pairs_directed_mma_kernel",
+                     "achieved": 8.0 * 0.5 * (hi - lo) * s * float(N) * N / (directed * 1e-3) / 1e12, "peak": fp32_peak,
+                     "unit": "TFLOP/s", "ms_per_launch": directed, "traffic": None},
+    }
+    out["roofline"]["frac"] = out["roofline"]["achieved"] / fp32_peak
+    if rank == 0 and world == 1:
+        from oracle import oracle as O
+        c = clouds[:32].cpu().numpy()
+        threads = host_threads() if O.have_ref() else 1
+        t0 = time.perf_counter()
+        npairs = 0
+        for i in range(32 if O.have_ref() else 2):
+            tgt = np.repeat(c[i][None], 32, axis=0)
+            if O.have_ref():
+                O.ref_nn_distance(c, tgt, threads)
+            else:
+                O.nn_distance(c, tgt, 0)
+            npairs += 32
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": npairs / dt, "unit": "cloud-pairs/s", "cores": threads,
+                               "kind": "reference" if O.have_ref() else "port",
+                               "sample": "%d cloud pairs (a 32-column block), both directions each" % npairs}
+    del clouds, cd, nn
+    return out
+
+
+def leg_knn(dev, world, rank, fp32_peak, flush, quick):
+    """configs[4]: defense kNN per-point distances (k=10), B=500 clouds of 2048 points split over the ranks,
+    result shards all-gathered (defender/get_knn_dists_per_point.py:74-81,116-119)."""
+    import torch
+    from geometric_adv_b200 import sharding
+    import geometric_adv_b200 as ga
+    b = 64 if quick else KNN_B
+    rng = np.random.default_rng(4)
+    pc = torch.from_numpy((rng.random((b, N, 3), dtype=np.float32) - np.float32(0.5)).astype(np.float32)).to(dev)
+    lo, hi = sharding.shard_range(b, world, rank)
+    mine = pc[lo:hi].contiguous()
+    for _ in range(3):
+        sharding.knn_dists_sharded(pc, KNN_K)
+    torch.cuda.synchronize()
+    reps = 10
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+    for r in range(reps):
+        flush.zero_()
+        ev[r][0].record()
+        part = ga.knn_dists(mine, KNN_K)
+        ev[r][1].record()
+        full = sharding.all_gather_rows(part, b)
+        ev[r][2].record()
+    torch.cuda.synchronize()
+    t_k = sum(e[0].elapsed_time(e[1]) for e in ev) / reps
+    t_g = sum(e[1].elapsed_time(e[2]) for e in ev) / reps
+    t_all = sum(e[0].elapsed_time(e[2]) for e in ev) / reps
+    t_k, t_g, t_all = _max_over_ranks([t_k, t_g, t_all], dev, world)
+    out = {
+        "workload": "configs[4]: kNN per-point distances k=%d, B=%d clouds x %d points over %d GPU(s)" % (KNN_K, b, N, world),
+        "scaling": "strong", "ms": t_all, "clouds_per_s": b / (t_all * 1e-3),
+        "point_pairs_per_s": b * float(N) * N / (t_all * 1e-3),
+        "phases_ms": {"knn_kernel": t_k, "all_gather": t_g}, "gather_share": t_g / t_all,
+        "checks": {"ascending": bool((full[:, :, 1:] >= full[:, :, :-1]).all()), "shape": list(full.shape)},
+        "roofline": {"bound": "fp32", "kernel": "knn_kernel", "achieved": 8.0 * (hi - lo) * float(N) * N / (t_k * 1e-3) / 1e12,
+                     "peak": fp32_peak, "unit": "TFLOP/s", "ms_per_launch": t_k, "traffic": None},
+    }
+    out["roofline"]["frac"] = out["roofline"]["achieved"] / fp32_peak
+    if rank == 0 and world == 1:
+        from oracle import oracle as O
+        sample = pc[:4].cpu().numpy()
+        t0 = time.perf_counter()
+        O.knn_dists_numpy(sample, KNN_K)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 4 / dt, "unit": "clouds/s", "cores": 1, "kind": "port",
+                               "sample": "4 clouds through the reference's numpy path (--use_tf_knn 0: get_dist_mat + sort, "
+                                         "general_utils.py:94-106), restated with numpy"}
+    return out
+
+
+def leg_attack(dev, world, rank, quick):
+    """configs[2]: the full geometric attack, 25 sources x 10 targets = 250 pairs, 500 iterations each, pairs
+    sharded contiguously over the ranks, results all-gathered (src/adv_ae.py:155-251)."""
+    import torch
+    from geometric_adv_b200 import sharding
+    from geometric_adv_b200.attack import PointNetAE, attack_pairs
+    iters, thresh = (20, 10) if quick else (ATK_ITERS, ATK_THRESH)
+    npairs = ATK_SOURCES * ATK_TARGETS
+    torch.manual_seed(0)
+    ae = PointNetAE(N)
+    g = torch.Generator().manual_seed(5)
+    src = (torch.rand(ATK_SOURCES, N, 3, generator=g) - 0.5).repeat_interleave(ATK_TARGETS, dim=0)
+    tgt = (torch.rand(npairs, N, 3, generator=g) - 0.5)
+    lo, hi = sharding.shard_range(npairs, world, rank)
+    mine = hi - lo
+    nb = -(-mine // 50)
+    bs = -(-mine // nb)  # equal batches of at most 50 pairs
+    # warm-up: one short run (graph capture, cuDNN/cuBLAS plans)
+    attack_pairs(ae, src, tgt, batch_size=bs, num_iterations=4, num_iterations_thresh=2, device=str(dev))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mets, advs = attack_pairs(ae, src, tgt, batch_size=bs, num_iterations=iters, num_iterations_thresh=thresh,
+                              device=str(dev))
+    e1.record()
+    torch.cuda.synchronize()
+    (ms,) = _max_over_ranks([e0.elapsed_time(e1)], dev, world)
+    return {
+        "workload": "configs[2]: geometric attack, %d x %d = %d pairs, %d iterations, PointNet AE random init, pairs over "
+                    "%d GPU(s) in batches of %d" % (ATK_SOURCES, ATK_TARGETS, npairs, iters, world, bs),
+        "scaling": "strong", "seconds": ms * 1e-3, "pair_iterations_per_s": npairs * iters / (ms * 1e-3),
+        "steps_per_s": nb * iters / (ms * 1e-3), "batch_size": bs, "batches_per_gpu": nb,
+        "checks": {"metrics_shape": list(mets.shape), "finite": bool(torch.isfinite(mets).all()),
+                   "moved": bool((advs.to(dev) - src.to(dev)).abs().amax() > 0)},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-attack", dest="no_attack", action="store_true", help="skip the attack steps/s leg")
+    ap.add_argument("--no-attack", dest="no_attack", action="store_true", help="skip the attack steps/s legs")
+    ap.add_argument("--no-legs", dest="no_legs", action="store_true", help="skip the config 3/4/5 legs")
+    ap.add_argument("--quick", action="store_true", help="small legs (development)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

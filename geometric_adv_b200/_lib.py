@@ -41,6 +41,8 @@ SIGNATURES = {
     "ga_chamfer_per_cloud": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "ga_chamfer_all_pairs": (_i, [_i, _i, _p, _i, _i, _p, _i, _p]),
     "ga_chamfer_all_pairs_directed": (_i, [_i, _i, _p, _i, _i, _p, _i, _p]),
+    "ga_symmetrize_rows": (_i, [_i, _i, _i, _p, _p, _p]),
+    "ga_sort_dist_mat": (_i, [_i, _i, _p, _i, _p, _i, _p, _p]),
     "ga_knn": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ga_knn_host": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "ga_selection_sort": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),

@@ -245,12 +245,12 @@ static int issue_pipeline(const FwdBwdBufs& f, int b, int n, int m, int mode, in
                               f.d_i2 + o2, f.d_o1 + o1 * 3, f.d_o2 + o2 * 3, (ga_stream_t)sk));
     GA_CUDA_TRY(cudaEventRecord(ev_b[ch], sk));
 
-    if (!f.mirror) {
+    if (!f.mirror && (f.dist1 || f.idx1 || f.dist2 || f.idx2)) {  // a NULL output is not copied back
       GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_f[ch], 0));
-      GA_CUDA_TRY(cudaMemcpyAsync(f.dist1 + o1, f.d_d1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
-      GA_CUDA_TRY(cudaMemcpyAsync(f.idx1 + o1, f.d_i1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
-      GA_CUDA_TRY(cudaMemcpyAsync(f.dist2 + o2, f.d_d2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
-      GA_CUDA_TRY(cudaMemcpyAsync(f.idx2 + o2, f.d_i2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
+      if (f.dist1) GA_CUDA_TRY(cudaMemcpyAsync(f.dist1 + o1, f.d_d1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
+      if (f.idx1) GA_CUDA_TRY(cudaMemcpyAsync(f.idx1 + o1, f.d_i1 + o1, c1 * 4, cudaMemcpyDeviceToHost, sout));
+      if (f.dist2) GA_CUDA_TRY(cudaMemcpyAsync(f.dist2 + o2, f.d_d2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
+      if (f.idx2) GA_CUDA_TRY(cudaMemcpyAsync(f.idx2 + o2, f.d_i2 + o2, c2 * 4, cudaMemcpyDeviceToHost, sout));
     }
     GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_b[ch], 0));
     GA_CUDA_TRY(cudaMemcpyAsync(f.gx1 + o1 * 3, f.d_o1 + o1 * 3, c1 * 12, cudaMemcpyDeviceToHost, sout));
@@ -419,7 +419,7 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
   // box it is NOT faster than the copy engines (ingest kernel 36 GB/s vs 43 GB/s DMA; gradients
   // written over PCIe by the SMs 30 GB/s vs 45 GB/s DMA; whole step 284 us vs 266 us), so the
   // default stays with cudaMemcpyAsync.
-  if (g_host_path == 2 && n > 0 && m > 0 && device_can_touch(xyz1) && device_can_touch(xyz2) && device_can_touch(grad_dist1) &&
+  if (g_host_path == 2 && n > 0 && m > 0 && dist1 && idx1 && dist2 && idx2 && device_can_touch(xyz1) && device_can_touch(xyz2) && device_can_touch(grad_dist1) &&
       device_can_touch(grad_dist2) && device_can_touch(dist1) && device_can_touch(idx1) &&
       device_can_touch(dist2) && device_can_touch(idx2) && device_can_touch(grad_xyz1) &&
       device_can_touch(grad_xyz2)) {
@@ -444,11 +444,17 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
     GA_CUDA_TRY(cudaGetDevice(&dev));
     HostGraph& G = graph_slot(dev, b, n, m, mode, key);
     G.seen++;
-    if (!G.failed && G.exec == nullptr && (G.seen >= 2 || g_host_graph == 2)) {
-      bool all_pinned = true;
-      for (int i = 0; all_pinned && i < 10; i++) all_pinned = is_pinned(key[i]);
-      G.failed = !all_pinned;
-      if (all_pinned) {
+    // Pinned status is re-checked on EVERY call (10 attribute look-ups, well under a microsecond each): a
+    // caller may free a pinned buffer and get pageable memory back at the same address, and the captured
+    // copy nodes would then DMA from unpinned pages.  Outputs 4..7 (dist/idx) may be NULL = not wanted.
+    bool all_pinned = true;
+    for (int i = 0; all_pinned && i < 10; i++) all_pinned = (key[i] == nullptr && i >= 4 && i < 8) || is_pinned(key[i]);
+    if (!all_pinned && G.exec != nullptr) {
+      cudaGraphExecDestroy(G.exec);
+      G.exec = nullptr;
+    }
+    if (all_pinned && !G.failed && G.exec == nullptr && (G.seen >= 2 || g_host_graph == 2)) {
+      {
         // Measured on the B200 box (profiles/r01_tune_e2e.json, B x 2048 x 2048): every extra chunk
         // costs ~25 us of dependency hops between copy and compute nodes, so the overlap only pays
         // once: B=10 one chunk 93 us (direct path 113), B=50 two chunks 210 us (direct 239, one chunk
@@ -461,8 +467,8 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
         // while it searches, which saves four copy nodes (B=10: 92 -> 81 us).  From 4 MB on the posted
         // PCIe writes slow the kernel more than the copies cost (B=50: 208 vs 216 us, B=200: 575 vs 657).
         const bool mirror = (g_host_graph_mirror == 2 || (g_host_graph_mirror == 0 && traffic < ((size_t)4 << 20))) &&
-                            device_can_touch(dist1) && device_can_touch(idx1) && device_can_touch(dist2) &&
-                            device_can_touch(idx2);
+                            dist1 && idx1 && dist2 && idx2 && device_can_touch(dist1) && device_can_touch(idx1) &&
+                            device_can_touch(dist2) && device_can_touch(idx2);
         FwdBwdBufs f = {xyz1, xyz2, grad_dist1, grad_dist2, dist1, dist2, grad_xyz1, grad_xyz2, idx1, idx2,
                         d_x1, d_x2, d_g1, d_g2, d_d1, d_d2, d_o1, d_o2, d_i1, d_i2, mirror};
         if (capture_pipeline(G, f, b, n, m, mode, nc) != GA_OK) G.failed = true;  // fall through to the direct path
@@ -504,13 +510,13 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
     GA_TRY(ga_nn_distance_bwd(bc, n, m, d_x1 + o1 * 3, d_x2 + o2 * 3, d_g1 + o1, d_i1 + o1, d_g2 + o2, d_i2 + o2,
                               d_o1 + o1 * 3, d_o2 + o2 * 3, (ga_stream_t)s));
     if (c1) {
-      GA_CUDA_TRY(cudaMemcpyAsync(dist1 + o1, d_d1 + o1, c1 * 4, cudaMemcpyDeviceToHost, s));
-      GA_CUDA_TRY(cudaMemcpyAsync(idx1 + o1, d_i1 + o1, c1 * 4, cudaMemcpyDeviceToHost, s));
+      if (dist1) GA_CUDA_TRY(cudaMemcpyAsync(dist1 + o1, d_d1 + o1, c1 * 4, cudaMemcpyDeviceToHost, s));
+      if (idx1) GA_CUDA_TRY(cudaMemcpyAsync(idx1 + o1, d_i1 + o1, c1 * 4, cudaMemcpyDeviceToHost, s));
       GA_CUDA_TRY(cudaMemcpyAsync(grad_xyz1 + o1 * 3, d_o1 + o1 * 3, c1 * 12, cudaMemcpyDeviceToHost, s));
     }
     if (c2) {
-      GA_CUDA_TRY(cudaMemcpyAsync(dist2 + o2, d_d2 + o2, c2 * 4, cudaMemcpyDeviceToHost, s));
-      GA_CUDA_TRY(cudaMemcpyAsync(idx2 + o2, d_i2 + o2, c2 * 4, cudaMemcpyDeviceToHost, s));
+      if (dist2) GA_CUDA_TRY(cudaMemcpyAsync(dist2 + o2, d_d2 + o2, c2 * 4, cudaMemcpyDeviceToHost, s));
+      if (idx2) GA_CUDA_TRY(cudaMemcpyAsync(idx2 + o2, d_i2 + o2, c2 * 4, cudaMemcpyDeviceToHost, s));
       GA_CUDA_TRY(cudaMemcpyAsync(grad_xyz2 + o2 * 3, d_o2 + o2 * 3, c2 * 12, cudaMemcpyDeviceToHost, s));
     }
   }

@@ -354,10 +354,13 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
   const int* oth_idx = (side ? a.idx1 : a.idx2) + (size_t)batch * L;
   float* out = (side ? a.gxyz2 : a.gxyz1) + (size_t)batch * P * 3;
 
-  // Stage the partner cloud once (4 points per thread in flight).  The coordinates are inputs of the
-  // forward kernel too, so they may be read while that kernel is still finishing (programmatic
-  // dependent launch: this grid starts early and waits here); indices and upstream gradients come
-  // from the preceding kernels and are read after the wait.
+  // Launched as a programmatic dependent, this grid may start while the preceding kernel of the stream is
+  // still running.  Only the one-call entry (ga_nn_distance_fwd_bwd: a.ticket != nullptr) knows that this
+  // kernel is the library's own forward search, which merely READS the coordinates: there they are staged
+  // while the search finishes.  Behind any other kernel (ga_nn_distance_bwd is a public entry and any
+  // producer of xyz / grad_dist may precede it) nothing is read before the grid dependency resolves.
+  if (a.ticket == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Stage the partner cloud once (4 points per thread in flight).
   for (int e0 = tid; e0 < L; e0 += 4 * T) {
     float px[4], py[4], pz[4];
 #pragma unroll
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
   }
   __syncthreads();
   const bool early = early_flag != 0;
-  if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!early && a.ticket != nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int e0 = tid; e0 < L; e0 += 4 * T) {
     int pk[4];
 #pragma unroll
@@ -553,7 +556,7 @@ int g_bwd_split = -1;  // tuning hook (key 9): -1 auto, 0 one CTA per cloud, 1 o
 
 namespace ga {
 static thread_local int t_gd_final = 0;  // set by ga_nn_distance_fwd_bwd around its gradient launch
-}
+}  // namespace ga
 
 extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const float* xyz2,
                                   const float* grad_dist1, const int* idx1, const float* grad_dist2,
@@ -606,14 +609,18 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
     a.call_id = 0;
     a.expected = 0;
     {
-      const LastForward& lf = last_forward();
-      if (g_pdl && lf.call_id != 0 && lf.stream == st && lf.idx1 == idx1 && lf.idx2 == idx2 && lf.b == b && lf.n == n &&
-          lf.m == m) {
+      // Tickets are honoured only inside ga_nn_distance_fwd_bwd (t_gd_final), where the library itself launched
+      // the search immediately before on this stream; the record is consumed by the first gradient launch
+      // that looks at it, so a stale ticket can never be matched by a later, unrelated call.
+      LastForward& lf = last_forward();
+      if (g_pdl && t_gd_final && lf.call_id != 0 && lf.stream == st && lf.idx1 == idx1 && lf.idx2 == idx2 && lf.b == b &&
+          lf.n == n && lf.m == m) {
         a.ticket = lf.ticket;
         a.call_id = lf.call_id;
         a.expected = lf.expected;
         a.ticket_debug = g_tickets == 2;
       }
+      lf.call_id = 0;
     }
     static std::atomic<unsigned> done2{0};
     int dev = 0;

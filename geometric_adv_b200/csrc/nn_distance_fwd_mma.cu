@@ -41,9 +41,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
   if (a.ticket != nullptr) {
     // one thread clears the slot and then triggers for the CTA; the others go straight to work (a barrier
     // here would put the ~1 us of the atomic and the fence in front of every CTA)
+    // Only the FIRST CTA of a batch element clears: a sibling that starts in a later wave must not erase the
+    // check-ins of siblings that have already finished (the count would never reach its target and the
+    // gradient kernel would fall back to the grid dependency after its spin).  Dependents cannot run before
+    // every CTA has passed its trigger below, i.e. before every clear is done.
     if (threadIdx.x == 0) {
       const int jpb0 = a.tiles1 + a.tiles2;
-      atomicExch(a.ticket + ticket_slot(a.call_id, (int)(blockIdx.x / jpb0)), a.call_id << 16);
+      if (blockIdx.x % jpb0 == 0) atomicExch(a.ticket + ticket_slot(a.call_id, (int)(blockIdx.x / jpb0)), a.call_id << 16);
       if (a.ticket_debug) atomicMax(a.ticket + kTicketSlots + 4, global_ns());  // start of the last CTA
       __threadfence();
       asm volatile("griddepcontrol.launch_dependents;");

@@ -45,6 +45,10 @@ def all_gather_rows(block, total_rows, group=None):
         return block
     sizes = [shard_range(total_rows, world, r) for r in range(world)]
     maxrows = max(hi - lo for lo, hi in sizes)
+    if total_rows % world == 0 and block.is_cuda:  # equal blocks: one NCCL all-gather straight into the result
+        out = torch.empty((total_rows,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(out, block.contiguous(), group=group)
+        return out
     pad = torch.zeros((maxrows,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
     pad[: block.shape[0]] = block
     parts = [torch.empty_like(pad) for _ in range(world)]
@@ -87,6 +91,99 @@ def sort_dist_mat(dist_mat, slice_idx):
     return nn_idx
 
 
+def sort_dist_mat_gpu(dist_rows, slice_idx):
+    """sort_dist_mat (prepare_indices_for_attack.py:167-180) on the GPU for a block of rows of the
+    Chamfer matrix: dist_rows (rows,S) CUDA float32 -> nn_idx (rows,S) int16 (class-local indices,
+    stable order).  Bit-identical to ``sort_dist_mat`` above on the same rows."""
+    from . import _lib
+    lib = _lib.load()
+    if dist_rows.device.type != "cuda" or dist_rows.dtype != torch.float32 or dist_rows.dim() != 2:
+        raise ValueError("sort_dist_mat_gpu expects a (rows,S) CUDA float32 tensor")
+    dist_rows = dist_rows.contiguous()
+    rows, s = dist_rows.shape
+    sl = [int(x) for x in slice_idx]
+    if sl[0] != 0 or sl[-1] != s or any(b < a for a, b in zip(sl[:-1], sl[1:])):
+        raise ValueError("slice_idx must run from 0 to S in non-decreasing steps")
+    nclass = len(sl) - 1
+    max_class = max([b - a for a, b in zip(sl[:-1], sl[1:])] + [0])
+    sl_dev = torch.tensor(sl, dtype=torch.int32, device=dist_rows.device)
+    nn_idx = torch.empty((rows, s), dtype=torch.int16, device=dist_rows.device)
+    with torch.cuda.device(dist_rows.device):
+        _lib.check(lib.ga_sort_dist_mat(s, rows, dist_rows.data_ptr(), nclass, sl_dev.data_ptr(), max_class,
+                                        nn_idx.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return nn_idx
+
+
+def symmetrize_rows(directed, row0, rows):
+    """Rows [row0, row0+rows) of CD = D + D^T from the gathered (S,S) matrix of directed terms."""
+    from . import _lib
+    lib = _lib.load()
+    directed = directed.contiguous()
+    s = directed.shape[0]
+    out = torch.empty((rows, s), dtype=torch.float32, device=directed.device)
+    with torch.cuda.device(directed.device):
+        _lib.check(lib.ga_symmetrize_rows(s, row0, rows, directed.data_ptr(), out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def prepare_indices(clouds, slice_idx, group=None, mode=None, timings=None):
+    """get_chamfer_nn of attacker/prepare_indices_for_attack.py:104-164 for the whole test set, sharded by row
+    blocks: returns (chamfer_dist_mat (S,S) float32, chamfer_nn_idx (S,S) int16), both complete on every rank.
+
+    rank r: directed terms D[i -> j] for its rows i (the tensor-core all-pairs kernel) -> ONE all-gather of
+    the row blocks (the only exchange the problem has; 16 MB for 2,000 shapes) -> its rows of CD = D + D^T ->
+    per-class stable argsort of its rows (ga_sort_dist_mat) -> all-gather of the finished rows.
+    `timings`, if a dict, receives CUDA-event milliseconds per phase."""
+    from . import ops
+    s = clouds.shape[0]
+    world, rank = _world(group)
+    lo, hi = shard_range(s, world, rank)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
+
+    def mark(i):
+        if ev is not None:
+            ev[i].record()
+
+    mark(0)
+    block = ops.chamfer_all_pairs(clouds, lo, hi - lo, mode=mode, directed=True)
+    mark(1)
+    d = all_gather_rows(block, s, group)
+    mark(2)
+    cd_rows = symmetrize_rows(d, lo, hi - lo)
+    nn_rows = sort_dist_mat_gpu(cd_rows, slice_idx)
+    mark(3)
+    cd = all_gather_rows(cd_rows, s, group)
+    nn_idx = all_gather_rows(nn_rows, s, group)
+    mark(4)
+    if ev is not None:
+        torch.cuda.synchronize(clouds.device)
+        for name, i in (("directed_ms", 0), ("gather_directed_ms", 1), ("symmetrize_sort_ms", 2),
+                        ("gather_results_ms", 3)):
+            timings[name] = ev[i].elapsed_time(ev[i + 1])
+        timings["total_ms"] = ev[0].elapsed_time(ev[4])
+    return cd, nn_idx
+
+
+def nearest_targets_gpu(nn_idx, slice_idx, num_targets):
+    """The attack's view of nn_idx for EVERY (source shape, target class) at once (src/adversary_utils.py:51-63):
+    out (S, nclass, num_targets) int16, the `num_targets` nearest instances of each target class (class-local
+    indices); for the shape's own class entry 0 (the shape itself) is skipped; -1 where a class is too small."""
+    s = nn_idx.shape[0]
+    sl = [int(x) for x in slice_idx]
+    nclass = len(sl) - 1
+    dev = nn_idx.device
+    starts = torch.tensor(sl[:-1], device=dev)
+    sizes = torch.tensor([b - a for a, b in zip(sl[:-1], sl[1:])], device=dev)
+    row_class = torch.bucketize(torch.arange(s, device=dev), torch.tensor(sl[1:], device=dev), right=True)
+    skip = (row_class[:, None] == torch.arange(nclass, device=dev)[None, :]).long()          # (S, nclass)
+    k = torch.arange(num_targets, device=dev)[None, None, :] + skip[:, :, None]              # (S, nclass, T)
+    ok = k < sizes[None, :, None]
+    cols = (starts[None, :, None] + k).clamp_(max=max(s - 1, 0))
+    out = torch.gather(nn_idx, 1, cols.reshape(s, -1)).reshape(s, nclass, num_targets)
+    return torch.where(ok, out, torch.full_like(out, -1))
+
+
 def nearest_targets(nn_idx, slice_idx, source_class, source_instance, target_class, num_targets):
     """The consumer's view (src/adversary_utils.py:51-63): the `num_targets` nearest instances of
     `target_class` for one source shape (indices local to the class; same-class lookups drop
@@ -117,6 +214,30 @@ def shard_pairs(sources, targets, group=None):
     world, rank = _world(group)
     lo, hi = shard_range(sources.shape[0], world, rank)
     return sources[lo:hi], targets[lo:hi], (lo, hi)
+
+
+def save_sel_idx_rand(data_path, slice_idx, num_instance_per_class=100, seed=55, file_name_parts=("test", "set", "13l")):
+    """get_rand_idx (prepare_indices_for_attack.py:66-86): per class, the first `num_instance_per_class`
+    entries of a seeded permutation of its instances, int16, -1 padded, under the reference's file name
+    sel_idx_rand_<n>_<parts>.npy.  Uses numpy's legacy global generator exactly as the reference does
+    (np.random.seed(55) before every class), so the file is byte-identical to the reference's."""
+    import os
+    nclass = len(slice_idx) - 1
+    sel_idx = -1 * np.ones([nclass, num_instance_per_class], dtype=np.int16)
+    state = np.random.get_state()
+    try:
+        for i in range(nclass):
+            np.random.seed(seed)
+            num_examples = int(slice_idx[i + 1] - slice_idx[i])
+            perm = np.arange(num_examples)
+            np.random.shuffle(perm)
+            num_instances = min(num_instance_per_class, num_examples)
+            sel_idx[i, :num_instances] = perm[:num_instance_per_class]
+    finally:
+        np.random.set_state(state)
+    path = os.path.join(data_path, "_".join(["sel_idx", "rand", "%d" % num_instance_per_class] + list(file_name_parts)) + ".npy")
+    np.save(path, sel_idx)
+    return path
 
 
 def save_chamfer_nn_files(data_path, chamfer_dist_mat, slice_idx, file_name_parts=("test", "set", "13l")):

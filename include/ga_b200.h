@@ -21,8 +21,16 @@
  *     positive cudaError_t.  ga_last_error() gives the message for the calling
  *     thread.  (The reference does no CUDA error checking, chamfer3D.cu:145-151
  *     only printf()s.)
- *   - Re-entrant; no global mutable state except the per-thread error string and
- *     a per-thread pinned staging arena used by the *_host entry points.
+ *   - Re-entrant: entry points may be called concurrently from several threads and on several
+ *     streams (tests/test_concurrency_gpu.py).  State: the per-thread error string, last-kernel
+ *     name and staging arena / graph cache of the *_host entry points; a per-device completion
+ *     ticket array (a slot overwritten by a concurrent call can only delay a ticket, never fake
+ *     one); and the ga_set_tuning() knobs, which are process-wide plain ints meant for
+ *     benchmarks and tests -- set them while no other thread is inside the library.
+ *   - The tensor-core filter window is relative to (max|q_c| + max|t_c|)^2, i.e. to the distance of
+ *     the clouds from the ORIGIN, not to their extent: clouds far from the origin relative to their
+ *     size (offset / extent above ~10) lose the filter's selectivity and run at the speed of the
+ *     exact scan (still bit-exact; timings in DESIGN.md "off-origin").  Centre such data first.
  */
 #ifndef GA_B200_H_
 #define GA_B200_H_
@@ -116,7 +124,9 @@ int ga_nn_distance_bwd_host(int b, int n, int m, const float* xyz1, const float*
                             float* grad_xyz2);
 
 /* Forward + backward in one host call (what one training / attack step does
- * with the op): HOST buffers in, HOST buffers out, one H2D and one D2H leg. */
+ * with the op): HOST buffers in, HOST buffers out, one H2D and one D2H leg.  Any of dist1 / idx1 /
+ * dist2 / idx2 may be NULL: that output is not copied back (the attack consumes only the gradients
+ * and a per-cloud loss on the host). */
 int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const float* xyz2,
                                 const float* grad_dist1, const float* grad_dist2, float* dist1, int* idx1,
                                 float* dist2, int* idx2, float* grad_xyz1, float* grad_xyz2, int mode);
@@ -138,6 +148,17 @@ int ga_chamfer_all_pairs(int s, int n, const float* clouds, int row0, int rows, 
  * (geometric_adv_b200/sharding.py). */
 int ga_chamfer_all_pairs_directed(int s, int n, const float* clouds, int row0, int rows, float* out, int mode,
                                   ga_stream_t stream);
+/* out (rows,s) = directed[row0 + r, j] + directed[j, row0 + r] for the gathered (s,s) matrix of directed
+ * terms: rows [row0, row0+rows) of the symmetric Chamfer matrix (chamfer_dist_mat, :139,151). */
+int ga_symmetrize_rows(int s, int row0, int rows, const float* directed, float* out, ga_stream_t stream);
+/* sort_dist_mat of attacker/prepare_indices_for_attack.py:167-180 for `rows` rows of the (.,s) Chamfer
+ * matrix: per target class c (columns [slice_idx[c], slice_idx[c+1]), slice_idx a DEVICE array of
+ * nclass+1 ints, max_class = the largest class) the class-local column indices in ascending order of
+ * distance, int16, into the same columns of nn_idx (rows,s) -- the array src/adversary_utils.py:51-63
+ * takes the attack targets from.  Stable (ties by ascending index, NaN last): np.argsort(kind="stable");
+ * the reference's default argsort leaves the order of exact ties unspecified. */
+int ga_sort_dist_mat(int s, int rows, const float* dist_rows, int nclass, const int* slice_idx_dev, int max_class,
+                     short* nn_idx, ga_stream_t stream);
 
 /* ---- grouping: knn_point / selection_sort / group_point ------------------- */
 /* knn_point(k, xyz1, xyz2) of tf_grouping.py:48-75 in ONE kernel: xyz1 (b,n,3) is the

@@ -170,3 +170,50 @@ def test_foldingnet_call_sites(ga):
         np.testing.assert_allclose(cov[i].cpu().numpy()[::50], c, rtol=1e-4, atol=1e-7)
     edges = callsites.knn_edges(idx)
     assert edges[0].shape[0] == 2 and edges[0].shape[1] >= 700 * 16
+
+
+def test_sort_dist_mat_gpu_equals_numpy_stable():
+    """ga_sort_dist_mat vs np.argsort(kind="stable") per class block, incl. exact ties, -0, inf and NaN."""
+    from geometric_adv_b200 import sharding
+    rng = np.random.default_rng(0)
+    s = 301
+    slice_idx = [0, 1, 1, 40, 173, 300, 301]  # an empty class, single-element classes, odd sizes
+    dm = rng.random((s, s)).astype(np.float32)
+    dm[rng.random((s, s)) < 0.2] = np.float32(0.25)            # many exact ties
+    dm[rng.random((s, s)) < 0.01] = np.float32(-0.0)
+    dm[rng.random((s, s)) < 0.01] = np.float32(0.0)
+    dm[5, 7] = np.inf
+    dm[9, 100:120] = np.nan
+    want = np.empty((s, s), np.int16)
+    for c in range(len(slice_idx) - 1):
+        a, b = slice_idx[c], slice_idx[c + 1]
+        want[:, a:b] = np.argsort(dm[:, a:b], axis=1, kind="stable")
+    got = sharding.sort_dist_mat_gpu(t(dm), slice_idx)
+    assert got.dtype == torch.int16 and np.array_equal(got.cpu().numpy(), want)
+    blk = sharding.sort_dist_mat_gpu(t(dm[17:60]), slice_idx)
+    assert np.array_equal(blk.cpu().numpy(), want[17:60])
+    big = rng.random((3, 5000)).astype(np.float32)              # one class of 5,000 shapes
+    got = sharding.sort_dist_mat_gpu(t(big), [0, 5000]).cpu().numpy()
+    assert np.array_equal(got, np.argsort(big, axis=1, kind="stable").astype(np.int16))
+
+
+def test_prepare_indices_pipeline(ga, tmp_path):
+    """Directed rows -> symmetrise -> per-class sort on the GPU == the host-side stage-file path."""
+    from geometric_adv_b200 import sharding
+    c = t(cloud(8, (45, 400, 3)))
+    slice_idx = [0, 10, 11, 30, 45]
+    cd, nn = sharding.prepare_indices(c, slice_idx, timings={})
+    full = ga.chamfer_all_pairs(c)
+    assert torch.equal(cd, full)
+    want = sharding.sort_dist_mat(full, slice_idx)
+    assert np.array_equal(nn.cpu().numpy(), want)
+    d = ga.chamfer_all_pairs(c, directed=True)
+    assert torch.equal(sharding.symmetrize_rows(d, 7, 20), full[7:27])
+    top = sharding.nearest_targets_gpu(nn, slice_idx, 5).cpu().numpy()
+    assert top.shape == (45, 4, 5)
+    for row, (sc, si) in [(3, (0, 3)), (10, (1, 0)), (29, (2, 18)), (44, (3, 14))]:
+        for tc in range(4):
+            w = sharding.nearest_targets(want, slice_idx, sc, si, tc, 5)
+            assert top[row, tc, :len(w)].tolist() == w.tolist() and np.all(top[row, tc, len(w):] == -1)
+    p1, p2 = sharding.save_chamfer_nn_files(str(tmp_path), cd, slice_idx)
+    assert np.array_equal(np.load(p2), nn.cpu().numpy())

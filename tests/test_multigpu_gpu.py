@@ -34,6 +34,10 @@ def _worker(rank, world, port, ret):
         dev = torch.device("cuda", rank)
         clouds = torch.from_numpy(cloud(3, (37, 512, 3))).to(dev)
         cd = sharding.all_pairs_chamfer(clouds)
+        sl = [0, 5, 20, 37]
+        cd2, nn2 = sharding.prepare_indices(clouds, sl)
+        clouds_even = torch.from_numpy(cloud(7, (16, 300, 3))).to(dev)  # equal blocks: all_gather_into_tensor path
+        cd3, nn3 = sharding.prepare_indices(clouds_even, [0, 9, 16])
         pc = torch.from_numpy(cloud(4, (21, 1024, 3))).to(dev)
         kd = sharding.knn_dists_sharded(pc, 10)
         torch.manual_seed(0)
@@ -44,6 +48,11 @@ def _worker(rank, world, port, ret):
             full = ga.chamfer_all_pairs(clouds)
             kd1 = ga.knn_dists(pc, 10)
             ret["cd_equal"] = bool(torch.equal(cd, full))
+            ret["prep_equal"] = bool(torch.equal(cd2, full)) and np.array_equal(
+                nn2.cpu().numpy(), sharding.sort_dist_mat(full, sl))
+            full3 = ga.chamfer_all_pairs(clouds_even)
+            ret["prep_even_equal"] = bool(torch.equal(cd3, full3)) and np.array_equal(
+                nn3.cpu().numpy(), sharding.sort_dist_mat(full3, [0, 9, 16]))
             ret["kd_equal"] = bool(torch.equal(kd, kd1))
             ret["attack"] = (m.cpu().numpy(), a.cpu().numpy())
         dist.barrier()
@@ -59,6 +68,7 @@ def test_two_rank_nccl_equals_single_gpu():
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert ret["cd_equal"], "sharded all-pairs matrix differs from the single-GPU one"
     assert ret["kd_equal"], "sharded kNN distances differ from the single-GPU ones"
+    assert ret["prep_equal"] and ret["prep_even_equal"], "sharded prepare_indices differs from the single-GPU files"
     from geometric_adv_b200.attack import PointNetAE, attack_pairs
     torch.manual_seed(0)
     ae = PointNetAE(256)

@@ -125,3 +125,22 @@ def test_stage_files_have_the_reference_names_and_dtypes(tmp_path):
     a, b = np.load(p1), np.load(p2)
     assert a.dtype == np.float32 and a.shape == (9, 9) and np.array_equal(a, dm)
     assert b.dtype == np.int16 and b.shape == (9, 9) and b.min() >= 0
+
+
+def test_sel_idx_rand_file(tmp_path):
+    """get_rand_idx (prepare_indices_for_attack.py:66-86): seeded permutation prefix per class, -1 padded."""
+    from geometric_adv_b200.sharding import save_sel_idx_rand
+    slice_idx = [0, 5, 130, 137]
+    before = np.random.get_state()[1][:4].copy()
+    path = save_sel_idx_rand(str(tmp_path), slice_idx, num_instance_per_class=100)
+    assert np.array_equal(np.random.get_state()[1][:4], before), "the caller's numpy RNG state must be left alone"
+    assert path.endswith("sel_idx_rand_100_test_set_13l.npy")
+    sel = np.load(path)
+    assert sel.dtype == np.int16 and sel.shape == (3, 100)
+    for i, n in enumerate([5, 125, 7]):
+        np.random.seed(55)
+        perm = np.arange(n)
+        np.random.shuffle(perm)
+        k = min(n, 100)
+        assert np.array_equal(sel[i, :k], perm[:k]) and np.all(sel[i, k:] == -1)
+        assert len(set(sel[i, :k].tolist())) == k
