@@ -30,6 +30,7 @@ extern int g_pdl;                // nn_distance_bwd.cu
 extern int g_pairs_kernel;       // all_pairs.cu
 extern int g_tickets;            // nn_distance_fwd_mma.cu
 extern int g_pairs_ablk;         // all_pairs.cu
+extern int g_umma_groups;        // nn_distance_fwd_umma.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -217,6 +218,10 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 19) {
     ga::g_pairs_ablk = value;
+    return GA_OK;
+  }
+  if (key == 20) {
+    ga::g_umma_groups = value;
     return GA_OK;
   }
   if (key == 11) {

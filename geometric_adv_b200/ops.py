@@ -127,7 +127,21 @@ def _nn_distance_fwd(xyz1, xyz2, mode):
 
 
 def nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
-    """NnDistanceGrad (tf_nndistance.cpp:84-166): returns grad_xyz1 (b,n,3), grad_xyz2 (b,m,3)."""
+    """NnDistanceGrad (tf_nndistance.cpp:84-166): returns grad_xyz1 (b,n,3), grad_xyz2 (b,m,3).
+    Dispatches through the registered custom op ``torch.ops.geometric_adv_b200.nn_distance_grad``."""
+    lib = _lib.load()
+    _lib.check(lib.ga_check_nn_distance_grad(
+        xyz1.dim(), _lib.dims(xyz1.shape), xyz2.dim(), _lib.dims(xyz2.shape),
+        grad_dist1.dim(), _lib.dims(grad_dist1.shape), idx1.dim(), _lib.dims(idx1.shape),
+        grad_dist2.dim(), _lib.dims(grad_dist2.shape), idx2.dim(), _lib.dims(idx2.shape)))
+    args = (_prep(xyz1, torch.float32, "xyz1"), _prep(xyz2, torch.float32, "xyz2"),
+            _prep(grad_dist1, torch.float32, "grad_dist1"), _prep(idx1, torch.int32, "idx1"),
+            _prep(grad_dist2, torch.float32, "grad_dist2"), _prep(idx2, torch.int32, "idx2"))
+    _same_device(*args)
+    return _nn_distance_grad_op(*args)
+
+
+def _nn_distance_grad_impl(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
     lib = _lib.load()
     _lib.check(lib.ga_check_nn_distance_grad(
         xyz1.dim(), _lib.dims(xyz1.shape), xyz2.dim(), _lib.dims(xyz2.shape),
@@ -157,26 +171,62 @@ def nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
     return g1, g2
 
 
-class _NnDistanceFn(torch.autograd.Function):
-    """Autograd glue: gradient only through dist1/dist2, idx non-differentiable
-    (tf_nndistance.py:35-41; dist_chamfer_3D.py:49-64)."""
+# ---- torch.library registration -------------------------------------------------------------------------------
+# The shim is a set of PyTorch custom ops (namespace geometric_adv_b200), not opaque Python: torch.compile / export
+# see them as single nodes with fake (meta) kernels for shape propagation, and autograd formulas registered on the
+# op itself.  The kernels behind them are the C ABI calls above; nothing is computed by torch.
+@torch.library.custom_op("geometric_adv_b200::nn_distance", mutates_args=())
+def _nn_distance_op(xyz1: torch.Tensor, xyz2: torch.Tensor, mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    return _nn_distance_fwd(xyz1, xyz2, mode)
 
-    @staticmethod
-    def forward(ctx, xyz1, xyz2, mode):
-        dist1, idx1, dist2, idx2 = _nn_distance_fwd(xyz1, xyz2, mode)
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
-        ctx.mark_non_differentiable(idx1, idx2)
-        return dist1, idx1, dist2, idx2
 
-    @staticmethod
-    def backward(ctx, grad_dist1, grad_idx1, grad_dist2, grad_idx2):
-        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        if grad_dist1 is None:
-            grad_dist1 = torch.zeros(idx1.shape, dtype=torch.float32, device=idx1.device)
-        if grad_dist2 is None:
-            grad_dist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=idx2.device)
-        g1, g2 = nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2)
-        return g1, g2, None
+@_nn_distance_op.register_fake
+def _(xyz1, xyz2, mode):
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    return (xyz1.new_empty((b, n)), xyz1.new_empty((b, n), dtype=torch.int32), xyz1.new_empty((b, m)),
+            xyz1.new_empty((b, m), dtype=torch.int32))
+
+
+@torch.library.custom_op("geometric_adv_b200::nn_distance_grad", mutates_args=())
+def _nn_distance_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_dist1: torch.Tensor, idx1: torch.Tensor,
+                         grad_dist2: torch.Tensor, idx2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    return _nn_distance_grad_impl(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2)
+
+
+@_nn_distance_grad_op.register_fake
+def _(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
+    return torch.empty_like(xyz1), torch.empty_like(xyz2)
+
+
+def _nn_distance_setup(ctx, inputs, output):
+    xyz1, xyz2, _mode = inputs
+    _d1, idx1, _d2, idx2 = output
+    ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+
+
+def _nn_distance_backward(ctx, grad_dist1, grad_idx1, grad_dist2, grad_idx2):
+    """Gradient only through dist1 / dist2; idx non-differentiable (tf_nndistance.py:35-41; dist_chamfer_3D.py:49-64)."""
+    xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+    if grad_dist1 is None:
+        grad_dist1 = torch.zeros(idx1.shape, dtype=torch.float32, device=idx1.device)
+    if grad_dist2 is None:
+        grad_dist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=idx2.device)
+    g1, g2 = _nn_distance_grad_op(xyz1, xyz2, grad_dist1.contiguous(), idx1, grad_dist2.contiguous(), idx2)
+    return g1, g2, None
+
+
+_nn_distance_op.register_autograd(_nn_distance_backward, setup_context=_nn_distance_setup)
+
+
+def _check_nn_distance_args(xyz1, xyz2):
+    lib = _lib.load()
+    _lib.check(lib.ga_check_nn_distance(xyz1.dim(), _lib.dims(xyz1.shape), xyz2.dim(), _lib.dims(xyz2.shape)))
+    for t, name in ((xyz1, "xyz1"), (xyz2, "xyz2")):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError("%s must be a torch.Tensor" % name)
+        if t.dtype != torch.float32:
+            raise TypeError("%s must be %s, got %s" % (name, torch.float32, t.dtype))
+    _same_device(xyz1, xyz2)
 
 
 def nn_distance(xyz1, xyz2, mode=None):
@@ -184,31 +234,21 @@ def nn_distance(xyz1, xyz2, mode=None):
 
     xyz1 (B,N,3), xyz2 (B,M,3) float32 -> dist1 (B,N) squared distance from each point of
     xyz1 to its nearest point of xyz2, idx1 (B,N) int32 its index, dist2 / idx2 the other
-    way.  Lowest index wins ties.  Differentiable through dist1 / dist2."""
+    way.  Lowest index wins ties.  Differentiable through dist1 / dist2.
+    Dispatches through the registered custom op ``torch.ops.geometric_adv_b200.nn_distance``."""
     mode = _default_mode if mode is None else mode
-    if not (torch.is_grad_enabled() and (xyz1.requires_grad or xyz2.requires_grad)):
-        return _nn_distance_fwd(xyz1, xyz2, mode)
-    return _NnDistanceFn.apply(xyz1, xyz2, mode)
+    _check_nn_distance_args(xyz1, xyz2)
+    return _nn_distance_op(xyz1.contiguous(), xyz2.contiguous(), int(mode))
 
 
-class chamfer_3DFunction(torch.autograd.Function):
-    """dist_chamfer_3D.py:26-64 -- same op, torch return order (dist1, dist2, idx1, idx2)."""
+class chamfer_3DFunction:
+    """dist_chamfer_3D.py:26-64 -- same op, torch return order (dist1, dist2, idx1, idx2).  Kept as a class with
+    ``apply`` because callers use ``chamfer_3DFunction.apply(a, b)``; the work is the registered custom op."""
 
     @staticmethod
-    def forward(ctx, xyz1, xyz2):
-        dist1, idx1, dist2, idx2 = _nn_distance_fwd(xyz1, xyz2, _default_mode)
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
-        ctx.mark_non_differentiable(idx1, idx2)
+    def apply(xyz1, xyz2):
+        dist1, idx1, dist2, idx2 = nn_distance(xyz1, xyz2)
         return dist1, dist2, idx1, idx2
-
-    @staticmethod
-    def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
-        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        if graddist1 is None:
-            graddist1 = torch.zeros(idx1.shape, dtype=torch.float32, device=idx1.device)
-        if graddist2 is None:
-            graddist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=idx2.device)
-        return nn_distance_grad(xyz1, xyz2, graddist1, idx1, graddist2, idx2)
 
 
 class chamfer_3DDist(torch.nn.Module):
@@ -272,10 +312,16 @@ def knn_point(k, xyz1, xyz2):
         raise ValueError("knn_point expects (batch_size, ndataset, 3) xyz1 and (batch_size, npoint, 3) xyz2")
     if xyz1.shape[0] != xyz2.shape[0]:
         raise ValueError("knn_point expects xyz1 and xyz2 have same batch size")
-    dev = _same_device(xyz1, xyz2)
+    _same_device(xyz1, xyz2)
+    return _knn_point_op(int(k), xyz1, xyz2)
+
+
+@torch.library.custom_op("geometric_adv_b200::knn_point", mutates_args=())
+def _knn_point_op(k: int, xyz1: torch.Tensor, xyz2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    dev = xyz1.device
     b, n, _ = xyz1.shape
     m = xyz2.shape[1]
-    k = int(k)
     val = torch.empty((b, m, max(k, 0)), dtype=torch.float32, device=dev)
     idx = torch.empty((b, m, max(k, 0)), dtype=torch.int32, device=dev)
     if dev.type == "cuda":
@@ -286,6 +332,12 @@ def knn_point(k, xyz1, xyz2):
         rc = lib.ga_knn_host(b, n, m, k, xyz1.data_ptr(), xyz2.data_ptr(), val.data_ptr(), idx.data_ptr())
     _lib.check(rc)
     return val, idx
+
+
+@_knn_point_op.register_fake
+def _(k, xyz1, xyz2):
+    b, m = xyz2.shape[0], xyz2.shape[1]
+    return xyz1.new_empty((b, m, max(k, 0))), xyz1.new_empty((b, m, max(k, 0)), dtype=torch.int32)
 
 
 def select_top_k(k, dist):
@@ -306,30 +358,41 @@ def select_top_k(k, dist):
     return outi, out
 
 
-class _GroupPointFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, points, idx):
-        lib = _lib.load()
-        b, n, c = points.shape
-        _, m, ns = idx.shape
-        out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
-        with _Guard(points.device):
-            _lib.check(lib.ga_group_point(b, n, c, m, ns, points.data_ptr(), idx.data_ptr(), out.data_ptr(),
-                                          _stream(points)))
-        ctx.save_for_backward(idx)
-        ctx.shape = (b, n, c)
-        return out
+@torch.library.custom_op("geometric_adv_b200::group_point", mutates_args=())
+def _group_point_op(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
+    with _Guard(points.device):
+        _lib.check(lib.ga_group_point(b, n, c, m, ns, points.data_ptr(), idx.data_ptr(), out.data_ptr(),
+                                      _stream(points)))
+    return out
 
-    @staticmethod
-    def backward(ctx, grad_out):
-        # GroupPointGrad (tf_grouping_g.cu:61-78) is a scatter-add; no script differentiates through
-        # group_point, so this off-path gradient uses torch's index_add_.
-        (idx,) = ctx.saved_tensors
-        b, n, c = ctx.shape
-        g = torch.zeros((b * n, c), dtype=grad_out.dtype, device=grad_out.device)
-        flat = (idx.long() + torch.arange(b, device=idx.device).view(b, 1, 1) * n).reshape(-1)
-        g.index_add_(0, flat, grad_out.reshape(-1, c))
-        return g.view(b, n, c), None
+
+@_group_point_op.register_fake
+def _(points, idx):
+    return points.new_empty((idx.shape[0], idx.shape[1], idx.shape[2], points.shape[2]))
+
+
+def _group_point_setup(ctx, inputs, output):
+    points, idx = inputs
+    ctx.save_for_backward(idx)
+    ctx.shape = tuple(points.shape)
+
+
+def _group_point_backward(ctx, grad_out):
+    # GroupPointGrad (tf_grouping_g.cu:61-78) is a scatter-add; no script differentiates through
+    # group_point, so this off-path gradient uses torch's index_add_.
+    (idx,) = ctx.saved_tensors
+    b, n, c = ctx.shape
+    g = torch.zeros((b * n, c), dtype=grad_out.dtype, device=grad_out.device)
+    flat = (idx.long() + torch.arange(b, device=idx.device).view(b, 1, 1) * n).reshape(-1)
+    g.index_add_(0, flat, grad_out.reshape(-1, c))
+    return g.view(b, n, c), None
+
+
+_group_point_op.register_autograd(_group_point_backward, setup_context=_group_point_setup)
 
 
 def group_point(points, idx):
@@ -342,7 +405,7 @@ def group_point(points, idx):
     if dev.type != "cuda":
         raise ValueError("group_point expects CUDA tensors (the reference op has GPU kernels only, "
                          "tf_grouping.cpp:171)")
-    return _GroupPointFn.apply(points, idx)
+    return _group_point_op(points, idx)
 
 
 def knn_dists(pc, k):
@@ -353,8 +416,13 @@ def knn_dists(pc, k):
     pc = _prep(pc.detach(), torch.float32, "pc")
     if pc.dim() != 3 or pc.shape[2] != 3:
         raise ValueError("knn_dists expects (batch_size, num_points, 3)")
+    return _knn_dists_op(pc, int(k))
+
+
+@torch.library.custom_op("geometric_adv_b200::knn_dists", mutates_args=())
+def _knn_dists_op(pc: torch.Tensor, k: int) -> torch.Tensor:
+    lib = _lib.load()
     b, n, _ = pc.shape
-    k = int(k)
     out = torch.empty((b, n, max(k, 0)), dtype=torch.float32, device=pc.device)
     if pc.device.type == "cuda":
         with _Guard(pc.device):
@@ -363,3 +431,8 @@ def knn_dists(pc, k):
         rc = lib.ga_knn_dists_host(b, n, k, pc.data_ptr(), out.data_ptr())
     _lib.check(rc)
     return out
+
+
+@_knn_dists_op.register_fake
+def _(pc, k):
+    return pc.new_empty((pc.shape[0], pc.shape[1], max(k, 0)))

@@ -99,3 +99,25 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libga_b200.so")
     with pytest.raises(_lib.GaError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_ops_are_registered_with_torch_library():
+    """The shim is a set of PyTorch custom ops (north_star: "PyTorch custom-op shim"): registered schemas and fake
+    kernels that propagate shapes / dtypes without touching a device."""
+    import torch
+    import geometric_adv_b200  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    ns = torch.ops.geometric_adv_b200
+    for name in ("nn_distance", "nn_distance_grad", "knn_point", "knn_dists", "group_point"):
+        assert hasattr(ns, name), name
+    assert "Tensor xyz1, Tensor xyz2, int mode" in str(ns.nn_distance.default._schema)
+    with FakeTensorMode():
+        a, b = torch.empty(3, 100, 3), torch.empty(3, 200, 3)
+        d1, i1, d2, i2 = ns.nn_distance(a, b, 0)
+        assert d1.shape == (3, 100) and i1.dtype == torch.int32 and d2.shape == (3, 200) and i2.shape == (3, 200)
+        g1, g2 = ns.nn_distance_grad(a, b, d1, i1, d2, i2)
+        assert g1.shape == a.shape and g2.shape == b.shape
+        val, idx = ns.knn_point(5, a, b)
+        assert val.shape == (3, 200, 5) and idx.dtype == torch.int32
+        assert ns.knn_dists(a, 10).shape == (3, 100, 10)
+        assert ns.group_point(a, idx).shape == (3, 200, 5, 3)

@@ -440,3 +440,20 @@ def test_chamfer_per_cloud(ga, oracle):
     got = ga.chamfer_per_cloud(d1, d2).cpu().numpy()
     want = oracle.chamfer_per_cloud(d1.cpu().numpy(), d2.cpu().numpy())
     np.testing.assert_allclose(got, want, rtol=2e-5)  # reduce_mean order is unpinned in the reference
+
+
+def test_custom_ops_pass_opcheck(ga):
+    """torch.library.opcheck: schema, fake kernel and autograd registration of the registered ops on real tensors."""
+    import torch
+    from torch.library import opcheck
+    a = torch.from_numpy(cloud(1, (2, 300, 3))).to(DEV).requires_grad_(True)
+    b = torch.from_numpy(cloud(2, (2, 257, 3))).to(DEV).requires_grad_(True)
+    opcheck(torch.ops.geometric_adv_b200.nn_distance.default, (a, b, 0),
+            test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    d1, i1, d2, i2 = ga.nn_distance(a, b)
+    assert d1.requires_grad and not i1.requires_grad
+    (d1.sum() + d2.sum()).backward()
+    assert a.grad is not None and b.grad is not None
+    opcheck(torch.ops.geometric_adv_b200.knn_point.default, (5, a.detach(), b.detach()),
+            test_utils=("test_schema", "test_faketensor"))
+    opcheck(torch.ops.geometric_adv_b200.knn_dists.default, (a.detach(), 4), test_utils=("test_schema", "test_faketensor"))
