@@ -14,7 +14,7 @@
 // chamfer_per_cloud_kernel, reduce.cu), so the matrix is bit-identical whichever kernel,
 // block size or row split produced it, and bit-identical to
 // ga_chamfer_per_cloud(ga_nn_distance_fwd(...)).  (The reference's own reduce_mean order
-// is unpinned: tolerance 1e-6 against the oracle.)
+// is unpinned: tolerance 1e-6 in the tests.)
 #include <atomic>
 
 #include "nn_mma.cuh"

@@ -31,6 +31,7 @@ extern int g_pairs_kernel;       // all_pairs.cu
 extern int g_tickets;            // nn_distance_fwd_mma.cu
 extern int g_pairs_ablk;         // all_pairs.cu
 extern int g_umma_groups;        // nn_distance_fwd_umma.cu
+extern int g_umma_auto;          // nn_distance_fwd.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -222,6 +223,10 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 20) {
     ga::g_umma_groups = value;
+    return GA_OK;
+  }
+  if (key == 21) {
+    ga::g_umma_auto = value;
     return GA_OK;
   }
   if (key == 11) {

@@ -270,6 +270,27 @@ int launch_fwd_mma_persist(const FwdArgs& a, int mode, cudaStream_t st);  // nn_
 int launch_fwd_mma_balanced(const FwdArgs& a, int mode, cudaStream_t st); // nn_distance_fwd_mma.cu
 int launch_fwd_umma(const FwdArgs& a, int mode, cudaStream_t st);         // nn_distance_fwd_umma.cu
 bool fwd_umma_supported(int n, int m);                                    // nn_distance_fwd_umma.cu
+extern thread_local int t_want_tickets;                                   // nn_distance_fwd_mma.cu
+int g_umma_auto = 1;  // tuning hook (key 21): 0 = never pick the tcgen05 kernel automatically
+
+// Tensor-core kernel of choice for a batch the HMMA kernel qualifies for.  The HMMA grid kernel (512-query CTAs, two
+// per SM) moves in steps of whole CTA rounds per SM: 28.6 us up to 148 CTAs, ~43 us up to 296, ~56 us up to 444
+// (2048-point clouds; B = 16 costs what B = 18 does and B = 19 what B = 37 does).  The persistent tcgen05 kernel
+// splits the same work into 128-query jobs, equal shares per SM, ~12 us + 4.5 us per job of an SM, so it wins on the
+// near side of every HMMA step and loses on the far side (profiles/r02_tune_fwd_sweep.txt: B = 4 18.4 vs 22.4 us,
+// 8 22.5 vs 26.6, 10 25.6 vs 28.6, 16 30.6 vs 28.6, 20 34.8 vs 40.9, 25 38.8 vs 41.0, 32 45.0 vs 43.9, 40 53.2 vs
+// 55.3, 50 61.4 vs 57.3).  Both times scale with the size of the target clouds.  The one-call entry keeps the HMMA
+// kernel: only that one checks in on the completion tickets the gradient kernel starts early from.
+static bool prefer_umma(int b, int n, int m) {
+  if (!fwd_umma_supported(n, m) || t_want_tickets) return false;
+  const long long jobs = (long long)b * ((n + 127) / 128 + (m + 127) / 128);
+  const long long ctas = (long long)b * ((n + 511) / 512 + (m + 511) / 512);
+  const int sms = sm_count();
+  const double scale = 0.5 * ((double)n + m) / 2048.0;  // both kernels' per-unit cost follows the target cloud size
+  const double t_umma = 12.0 + 4.5 * scale * (double)((jobs + sms - 1) / sms);
+  const double t_hmma = 14.5 + 14.0 * scale * (double)((ctas + sms - 1) / sms);
+  return t_umma + 0.5 < t_hmma;
+}
 
 }  // namespace ga
 
@@ -333,7 +354,7 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   int variant = g_fwd_variant;
   if (variant == 0) {
     const long long queries = (long long)b * ((long long)n + m);
-    variant = mma_auto ? 20 : (queries < 148LL * 2 * 512 ? 4 : 1);
+    variant = mma_auto ? (g_umma_auto && prefer_umma(b, n, m) ? 22 : 20) : (queries < 148LL * 2 * 512 ? 4 : 1);
   }
   if (variant == 20) return launch_fwd_mma(a, mode, st);
   if (variant == 21) return launch_fwd_mma_persist(a, mode, st);

@@ -210,7 +210,9 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  *   14 gradient kernel (0 auto = atomics + list sort, 1 = stable counting sort)   15 dependent launch (1)
  *   16 all-pairs kernel (0 auto = tensor-core scan, 1 = fp32 filter)   17 replay: dist/idx mirrored to the host
  *      (0 auto, 1 never, 2 always)   18 completion tickets (0 never, 1 one-call entry only, 2 always + debug, 3 always)
- *   19 all-pairs source clouds per CTA (0 auto)   20 tcgen05 kernel: warp groups per CTA (0 auto, 2, 4) */
+ *   19 all-pairs source clouds per CTA (0 auto)   20 tcgen05 kernel, development build: bit 0 no refine, bit 1 no
+ *      drain, bit 3 no helper, bits 8.. traced CTA (0 = product build)   21 automatic choice of the tcgen05 kernel
+ *      between the HMMA kernel's wave steps (1) */
 int ga_set_tuning(int key, int value);
 /* Empty-kernel launch floor in microseconds (average over `reps` launches). */
 int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);

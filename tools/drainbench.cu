@@ -32,8 +32,20 @@ __device__ __forceinline__ void fold(const float (&v)[32], int tile, float& c1, 
 }
 // MODE 0: loads only; 1: fold only (registers perturbed cheaply so nothing is hoisted); 2: double-buffered ld + fold
 // (the kernel's tc_drain); 3: single buffer ld -> wait -> fold
-template <int MODE>
-__global__ void __launch_bounds__(512) bench(float* out, int iters, long long* cyc) {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// MMA > 0: an extra warp (the last one) keeps issuing M128 N256 K16 bf16 MMAs into the accumulators the other warps
+// read (values do not matter), one per MMA clocks (1 = back to back), until the drain warps are done.
+template <int MODE, int MMA>
+__global__ void __launch_bounds__(544) bench(float* out, int iters, long long* cyc) {
+  extern __shared__ __align__(128) unsigned char opsm[];
+  __shared__ unsigned long long mbar;
+  __shared__ volatile int stop;
+  const int nscan = (blockDim.x >> 5) - (MMA ? 1 : 0);
+  if (MMA) {
+    for (int i = threadIdx.x; i < (128 * 32 + 2048 * 32) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(opsm)[i] = 0x3c003c00u + i;
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar))); stop = 0; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -43,6 +55,28 @@ __global__ void __launch_bounds__(512) bench(float* out, int iters, long long* c
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
+  if (MMA && warp == nscan) {
+    if ((threadIdx.x & 31) == 0) {
+      const uint32_t desc_hi = (uint32_t)(256 >> 4) | (1u << 14);
+      const uint32_t a_lo = ((smem_u32(opsm) & 0x3ffffu) >> 4) | ((uint32_t)(128 >> 4) << 16);
+      const uint32_t b_lo = ((smem_u32(opsm + 4096) & 0x3ffffu) >> 4) | ((uint32_t)(128 >> 4) << 16);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t phase = 0; unsigned n = 0;
+      while (!stop) {
+        const long long t0 = clock64();
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_base + (n & 1) * 256),
+                     "l"(((uint64_t)desc_hi << 32) | a_lo), "l"(((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)(n & 7) * (256 * 32 / 16))), "r"(idesc), "r"(0u) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+        uint32_t done = 0;
+        while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+        phase ^= 1; n++;
+        while (MMA > 1 && clock64() - t0 < MMA && !stop) {}
+      }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    return;
+  }
   const uint32_t base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ((warp >> 2) & 1) * 256;
   float c1 = 3e38f, c2 = 3e38f, c3 = 3e38f, acc = 0.f;
   float v[32], w[32];
@@ -76,17 +110,20 @@ __global__ void __launch_bounds__(512) bench(float* out, int iters, long long* c
     }
   }
   const long long t1 = clock64();
+  if (MMA) { asm volatile("bar.sync 1, %0;" ::"r"(nscan * 32)); if (threadIdx.x == 0) stop = 1; }
   if (c1 + c2 + c3 + acc + v[5] + w[7] == 123.456f) out[0] = c1;
   if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
-template <int MODE>
+template <int MODE, int MMA = 0>
 static void run(const char* name, int threads, int sms) {
   float* out; long long* cyc;
   CK(cudaMalloc(&out, 4)); CK(cudaMalloc(&cyc, 8));
   const int iters = 1 << 12;
-  for (int rep = 0; rep < 2; rep++) { bench<MODE><<<sms, threads>>>(out, iters, cyc); CK(cudaDeviceSynchronize()); }
+  const size_t sm = MMA ? 128 * 32 + 2048 * 32 : 0;
+  if (MMA) CK(cudaFuncSetAttribute(bench<MODE, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  for (int rep = 0; rep < 2; rep++) { bench<MODE, MMA><<<sms, threads + (MMA ? 32 : 0), sm>>>(out, iters, cyc); CK(cudaDeviceSynchronize()); }
   long long h = 0; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
   const int warps = threads / 32;
   const double per_tile_warp = (double)h / (iters * 8.0);
@@ -104,5 +141,12 @@ int main() {
     run<2>("ld + fold, double-buffered", th, sms);
     run<3>("ld -> wait -> fold", th, sms);
   }
+  printf("-- with an MMA stream (M128 N256 K16) into the accumulators being read --\n");
+  run<0, 1>("ld only, MMAs back to back", 512, sms);
+  run<1, 1>("fold only, MMAs back to back", 512, sms);
+  run<3, 1>("ld -> wait -> fold, MMAs back to back", 512, sms);
+  run<0, 400>("ld only, one MMA per 400 clk", 512, sms);
+  run<3, 400>("ld -> wait -> fold, one MMA per 400 clk", 512, sms);
+  run<3, 800>("ld -> wait -> fold, one MMA per 800 clk", 512, sms);
   return 0;
 }

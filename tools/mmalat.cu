@@ -19,7 +19,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
       : "r"(taddr) : "memory");
 }
-template <int N, int LOADERS>
+template <int N, int LOADERS, int BURST = 1>
 __global__ void __launch_bounds__(256) bench(float* out, int iters, long long* res) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base;
@@ -51,8 +51,10 @@ __global__ void __launch_bounds__(256) bench(float* out, int iters, long long* r
       uint32_t phase = 0;
       for (int it = 0; it < iters; it++) {
         const long long t0 = clock64();
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
-                     "l"(((uint64_t)desc_hi << 32) | a_lo), "l"(((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)(it & 3) * (N * 32 / 16))), "r"(idesc), "r"(0u) : "memory");
+#pragma unroll 1
+        for (int q = 0; q < BURST; q++)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem + (q & 1) * 256),
+                     "l"(((uint64_t)desc_hi << 32) | a_lo), "l"(((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)((it + q) & 3) * (N * 32 / 16))), "r"(idesc), "r"(0u) : "memory");
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         uint32_t done = 0;
         while (!done) {
@@ -67,6 +69,24 @@ __global__ void __launch_bounds__(256) bench(float* out, int iters, long long* r
       if (blockIdx.x == 0) { res[0] = tot; res[1] = mx; }
       stop = 1;
     }
+  } else if (LOADERS == 2) {  // warps 4-7 poll an mbarrier that never completes (what waiting warps of a pipeline do)
+    __shared__ unsigned long long idle_bar;
+    if (tid == 128) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&idle_bar)));
+    asm volatile("bar.sync 1, 128;");
+    uint32_t done = 0;
+    while (!stop) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&idle_bar)), "r"(0u) : "memory");
+    }
+    if (done == 123) out[0] = 1.f;
+  } else if (LOADERS == 3) {  // same with test_wait (pure spin)
+    __shared__ unsigned long long idle_bar2;
+    if (tid == 128) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&idle_bar2)));
+    asm volatile("bar.sync 1, 128;");
+    uint32_t done = 0;
+    while (!stop) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&idle_bar2)), "r"(0u) : "memory");
+    }
+    if (done == 123) out[0] = 1.f;
   } else if (LOADERS) {  // warps 4-7 drain the other accumulator all the time
     const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
     float acc = 0.f;
@@ -81,14 +101,14 @@ __global__ void __launch_bounds__(256) bench(float* out, int iters, long long* r
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
-template <int N, int LOADERS>
+template <int N, int LOADERS, int BURST = 1>
 static void run(const char* name, int sms) {
   float* out; long long* res;
   CK(cudaMalloc(&out, 4)); CK(cudaMalloc(&res, 16));
   const int iters = 2000;
   const size_t sm = 128 * 32 + 2048 * 32;
-  CK(cudaFuncSetAttribute(bench<N, LOADERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  for (int rep = 0; rep < 2; rep++) { bench<N, LOADERS><<<sms, 256, sm>>>(out, iters, res); CK(cudaDeviceSynchronize()); }
+  CK(cudaFuncSetAttribute(bench<N, LOADERS, BURST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  for (int rep = 0; rep < 2; rep++) { bench<N, LOADERS, BURST><<<sms, 256, sm>>>(out, iters, res); CK(cudaDeviceSynchronize()); }
   long long h[2]; CK(cudaMemcpy(h, res, 16, cudaMemcpyDeviceToHost));
   printf("%-44s issue -> barrier complete: avg %6.1f clk, max %lld\n", name, (double)h[0] / iters, h[1]);
   cudaFree(out); cudaFree(res);
@@ -101,5 +121,13 @@ int main() {
   run<128, 0>("M128 N128 K16, alone", p.multiProcessorCount);
   run<128, 1>("M128 N128 K16, 4 warps draining TMEM", p.multiProcessorCount);
   run<64, 0>("M128 N64 K16, alone", p.multiProcessorCount);
+  run<256, 2>("M128 N256 K16, 4 warps polling try_wait", p.multiProcessorCount);
+  run<256, 3>("M128 N256 K16, 4 warps polling test_wait", p.multiProcessorCount);
+  run<256, 2, 16>("M128 N256 K16 x16, 4 warps polling try_wait", p.multiProcessorCount);
+  run<256, 0, 2>("M128 N256 K16 x2 per commit", p.multiProcessorCount);
+  run<256, 0, 4>("M128 N256 K16 x4 per commit", p.multiProcessorCount);
+  run<256, 0, 16>("M128 N256 K16 x16 per commit", p.multiProcessorCount);
+  run<256, 1, 16>("M128 N256 K16 x16 per commit, 4 warps draining", p.multiProcessorCount);
+  run<128, 0, 16>("M128 N128 K16 x16 per commit", p.multiProcessorCount);
   return 0;
 }

@@ -18,7 +18,12 @@ for (B, N, M) in shapes:
     d1 = torch.empty(B, N, device=dev); i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
     d2 = torch.empty(B, M, device=dev); i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
     ref = None
-    for name, keys in (("hmma", {0: 20}), ("tc", {0: 22})):
+    only = os.environ.get("TUNE_ONLY")
+    for name, keys in (("default", {}), ("hmma", {0: 20}), ("tc", {0: 22}), ("tc_dev", {0: 22, 20: 16}), ("tc_norefine", {0: 22, 20: 1}), ("tc_nohelper", {0: 22, 20: 9}), ("tc_neither", {0: 22, 20: 3}), ("tc_nohelper_nodrain", {0: 22, 20: 11})):
+        if only and name not in only.split(','):
+            continue
+        if (keys.get(20, 0) & 8) and B > 100:
+            continue  # no helper: the stager would wait for ever on a third cloud
         for k, v in keys.items():
             lib.ga_set_tuning(k, v)
         def call():
