@@ -20,7 +20,7 @@
 //           list shows a tie (or NaN / missing entries), the query is replayed by a
 //           warp that simulates the selection sort on the only elements that can
 //           take part in it (positions < k, values < v_k, first k values == v_k).
-#include "nn_tiles.cuh"
+#include "nn_mma.cuh"
 
 namespace ga {
 
@@ -392,6 +392,387 @@ __global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// knn_mma_kernel: the same search with both filter scans on the tensor cores (k + 1 <= 12, data sets of
+// 512..2048 points, large batches: BASELINE config 5).
+//
+// A CTA of 16 warps stages one data set (pair-SoA + the B fragments of nn_mma.cuh, 96 KB) and serves 1024 queries,
+// one 64-query job per warp:
+//   scan 1  mma_scan_range<6>: every lane keeps the three smallest tile keys of the 16 tiles it owns per row; the
+//           quad's 4 x 3 = 12 keys belong to 12 different tiles, so their maximum tau bounds the 12-th smallest
+//           filter value of the row from above (12 >= k + 1 certified points).
+//   scan 2  the same MMA loop against thr = tau + W: a 64-bit mask per row of the tiles whose minimum passes
+//           (one compare per tile and row instead of the key tracking); 16 shuffles hand every lane the masks of the
+//           two queries it owns (rows 2t, 2t+1 of its quad: local queries 16 t + g + 8 j, as in nn_mma.cuh).
+//   walk    one query per lane at a time: the ~13-20 qualifying tiles are walked with the fp32 filter, candidates
+//           (f <= thr) go to the query's queue in shared memory (predicated stores, the warp stays in step).
+//           Lanes walk DIFFERENT tiles (512 B apart: same banks), so each lane starts at its own pair (lane & 15)
+//           and the upper half-warp loads the {z,n} half of a pair first: one LDS.128 of the warp then touches
+//           every bank once.  The two halves need different operands for the same FMA chain, hence the per-lane
+//           coefficient quadruple (cA1, cA2, cB1, cB2) = (ax, ay, az, 1) or (az, 1, ax, ay).
+//   drain   the queue is evaluated in the reference arithmetic and inserted into the exact sorted (k+1)-list;
+//           ties, NaN and overflow go to the replay exactly as in knn_kernel.
+// Bound: a point p of the reference's first k + 1 has d(p) <= max_c d(c) over the 12 certified points c, hence
+// (nn_mma.cuh: e0 reference rounding, e1 fp32 filter, e2 MMA filter, 384u key perturbation)
+//   h(p)   <= tau + 384u + 2 e2 + 2 e0 = tau + 1074u s^2   (tile mask)
+//   f32(p) <= tau + 384u + e2 + 2 e0 + e1 = tau + 763u s^2  (walk)
+// both below W = mma_window_wide = 2048u s^2.
+// ---------------------------------------------------------------------------
+constexpr int kKnnMmaWarps = 16;
+constexpr int kKnnMmaThreads = kKnnMmaWarps * 32;
+constexpr int kKnnMmaQT = kKnnMmaWarps * kMmaQW;  // 1024 queries per CTA
+constexpr int kKnnMmaCH = 2048;
+constexpr int kKnnMmaKL = 12;
+constexpr int kKnnMmaEnt = 20;  // queue entries (tile, 32-bit candidate mask) per query: ~13 tiles are walked (max ~20), most have a candidate
+constexpr size_t kKnnMmaOffRed = (size_t)kKnnMmaCH * 16 + (size_t)kPipeU * 32;
+constexpr size_t kKnnMmaOffB = kKnnMmaOffRed + 32 * 4;
+constexpr size_t kKnnMmaOffQueue = kKnnMmaOffB + (size_t)kKnnMmaCH * 32;
+constexpr size_t kKnnMmaOffQTile = kKnnMmaOffQueue + (size_t)kKnnMmaWarps * 2 * kKnnMmaEnt * 32 * 4;  // masks: [warp][2][ent][32] u32
+constexpr size_t kKnnMmaOffFlagQ = kKnnMmaOffQTile + (size_t)kKnnMmaWarps * 2 * kKnnMmaEnt * 32;       // tiles: [warp][2][ent][32] u8
+constexpr size_t kKnnMmaOffFlagV = kKnnMmaOffFlagQ + (size_t)kKnnMmaQT * 4;
+constexpr size_t kKnnMmaOffCnt = kKnnMmaOffFlagV + (size_t)kKnnMmaQT * 4;
+constexpr size_t kKnnMmaOffScratch = kKnnMmaOffCnt + 16;
+constexpr size_t kKnnMmaSmem = kKnnMmaOffScratch + (size_t)kKnnMmaWarps * 3 * kKnnMmaKL * 8;
+static_assert(kKnnMmaOffB % 16 == 0 && kKnnMmaOffQueue % 16 == 0 && kKnnMmaSmem <= 232448, "shared memory layout");
+
+__global__ void __launch_bounds__(kKnnMmaThreads, 1) knn_mma_kernel(const KnnArgs a) {
+  constexpr int KL = kKnnMmaKL, T = kMmaT;
+  const float kInf = __int_as_float(0x7f800000);
+  const float kNaN = __int_as_float(0x7fc00000);
+  extern __shared__ float4 smem_f4[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(smem_f4);
+  float4* tgt = smem_f4;
+  float* red = reinterpret_cast<float*>(smem + kKnnMmaOffRed);
+  uint4* bfrag = reinterpret_cast<uint4*>(smem + kKnnMmaOffB);
+  int* flag_q = reinterpret_cast<int*>(smem + kKnnMmaOffFlagQ);
+  float* flag_vk = reinterpret_cast<float*>(smem + kKnnMmaOffFlagV);
+  int* flag_cnt = reinterpret_cast<int*>(smem + kKnnMmaOffCnt);
+  unsigned char* scratch = smem + kKnnMmaOffScratch;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int batch = blockIdx.x / a.qtiles;
+  const int qtile = blockIdx.x - batch * a.qtiles;
+  const int n = a.n, k = a.k;
+  const float* pts = a.xyz1 + (size_t)batch * n * 3;
+  const float* qpts = a.xyz2 + (size_t)batch * a.m * 3;
+  const int kout = k - a.skip;
+  const bool need_idx = a.idx != nullptr;
+  if (tid == 0) *flag_cnt = 0;
+
+  // ---- stage the data set: warp w builds MMA block w (128 points) ----
+  const int nblk = (n + kMmaBlk - 1) / kMmaBlk, ntile = (n + T - 1) / T;
+  {
+    float lmax = 0.0f;
+    if (warp < nblk) lmax = stage_block_warp(tgt, bfrag, pts, n, warp, lane);
+    lmax = warp_max(lmax);
+    if (lane == 0) red[warp] = lmax;
+  }
+  __syncthreads();
+  float bm = 0.0f;
+#pragma unroll
+  for (int w = 0; w < kKnnMmaWarps; w++) bm = fmaxf(bm, red[w]);
+
+  const int qbase = qtile * kKnnMmaQT + warp * kMmaQW;
+  if (qbase < a.m) {
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned qb = lane & ~3;
+    MmaRows R;
+    mma_load_rows(R, qpts, a.m, qbase, lane);
+    // ---- scan 1: the four smallest tile minima per row among this lane's tiles -> tau per row ----
+    float thr[8];
+    {
+      float c1[8], c2[8], c3[8], c4[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) c1[r] = c2[r] = c3[r] = c4[r] = kMmaBig;
+      const uint2* bfr = reinterpret_cast<const uint2*>(bfrag);
+#pragma unroll 1
+      for (int blk = 0; blk < nblk; blk++) {
+        float rm[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) rm[r] = kMmaBig;
+        const uint2* bp = bfr + (size_t)blk * 16 * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const uint2 bf = bp[j * 32];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            float c[4];
+            mma16816(c, R.a[i], bf.x, bf.y);
+            rm[2 * i] = fmin3(rm[2 * i], c[0], c[1]);
+            rm[2 * i + 1] = fmin3(rm[2 * i + 1], c[2], c[3]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const float v = rm[r];
+          c4[r] = fminf(c4[r], fmaxf(c3[r], v));
+          c3[r] = fminf(c3[r], fmaxf(c2[r], v));
+          c2[r] = fminf(c2[r], fmaxf(c1[r], v));
+          c1[r] = fminf(c1[r], v);
+        }
+      }
+      // tau = the 12-th smallest of the quad's 4 x 4 values (12 different tiles hold a point with h <= tau, which
+      // covers every k + 1 <= 12): merge with the neighbour lane (bitonic, 4 + 4), then the 12-th of two sorted
+      // eights = min over i of max(A[i - 1], B[11 - i]), i = 4..8
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const float b0 = __shfl_xor_sync(0xffffffffu, c1[r], 1), b1 = __shfl_xor_sync(0xffffffffu, c2[r], 1),
+                    b2 = __shfl_xor_sync(0xffffffffu, c3[r], 1), b3 = __shfl_xor_sync(0xffffffffu, c4[r], 1);
+        const float l0 = fminf(c1[r], b3), l1 = fminf(c2[r], b2), l2 = fminf(c3[r], b1), l3 = fminf(c4[r], b0);
+        float h0 = fmaxf(c1[r], b3), h1 = fmaxf(c2[r], b2), h2 = fmaxf(c3[r], b1), h3 = fmaxf(c4[r], b0);
+        const float A3 = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));  // the 4-th smallest of the eight
+        // h0..h3 is bitonic: two compare-exchange stages sort it
+        float t0 = fminf(h0, h2), t2 = fmaxf(h0, h2), t1 = fminf(h1, h3), t3 = fmaxf(h1, h3);
+        const float A4 = fminf(t0, t1), A5 = fmaxf(t0, t1), A6 = fminf(t2, t3), A7 = fmaxf(t2, t3);
+        const float B3 = __shfl_xor_sync(0xffffffffu, A3, 2), B4 = __shfl_xor_sync(0xffffffffu, A4, 2),
+                    B5 = __shfl_xor_sync(0xffffffffu, A5, 2), B6 = __shfl_xor_sync(0xffffffffu, A6, 2),
+                    B7 = __shfl_xor_sync(0xffffffffu, A7, 2);
+        float tau = fminf(fmaxf(A3, B7), fmaxf(A4, B6));
+        tau = fminf(tau, fmaxf(A5, B5));
+        tau = fminf(tau, fminf(fmaxf(A6, B4), fmaxf(A7, B3)));
+        thr[r] = tau + mma_window_wide(R.qabs[r], bm);
+      }
+    }
+    // ---- scan 2: tile masks (bit blk of mk[r]: tile 4 blk + t of row r passes) ----
+    uint32_t pk[4];
+    {
+      uint32_t mk[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) mk[r] = 0;
+      const uint2* bfr = reinterpret_cast<const uint2*>(bfrag);
+#pragma unroll 1
+      for (int blk = 0; blk < nblk; blk++) {
+        float rm[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) rm[r] = kMmaBig;
+        const uint2* bp = bfr + (size_t)blk * 16 * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const uint2 bf = bp[j * 32];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            float c[4];
+            mma16816(c, R.a[i], bf.x, bf.y);
+            rm[2 * i] = fmin3(rm[2 * i], c[0], c[1]);
+            rm[2 * i + 1] = fmin3(rm[2 * i + 1], c[2], c[3]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) mk[r] |= !(rm[r] > thr[r]) ? (1u << blk) : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) pk[i] = mk[2 * i] | (mk[2 * i + 1] << 16);
+    }
+    // masks of this lane's two queries: w0 = tile columns 0 (low half) and 1 (high half), w1 = columns 2 and 3
+    uint32_t w0a = 0, w1a = 0, w0b = 0, w1b = 0;  // a: query j = 0, b: j = 1
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t p0 = __shfl_sync(0xffffffffu, pk[i], qb), p1 = __shfl_sync(0xffffffffu, pk[i], qb + 1),
+                     p2 = __shfl_sync(0xffffffffu, pk[i], qb + 2), p3 = __shfl_sync(0xffffffffu, pk[i], qb + 3);
+      if (i == t) {
+        w0a = (p0 & 0xffffu) | (p1 << 16);
+        w1a = (p2 & 0xffffu) | (p3 << 16);
+        w0b = (p0 >> 16) | (p1 & 0xffff0000u);
+        w1b = (p2 >> 16) | (p3 & 0xffff0000u);
+      }
+    }
+    const float thqa = t == 0 ? thr[0] : (t == 1 ? thr[2] : (t == 2 ? thr[4] : thr[6]));
+    const float thqb = t == 0 ? thr[1] : (t == 1 ? thr[3] : (t == 2 ? thr[5] : thr[7]));
+    // ---- walk: both queries of the lane in one loop; per tile a 32-bit candidate mask, queued as (tile, mask) ----
+    // queue of a query: kKnnMmaEnt entries, entry e of lane l at word e * 32 + l (masks) / byte e * 32 + l (tiles)
+    uint32_t* qmask = reinterpret_cast<uint32_t*>(smem + kKnnMmaOffQueue) + (size_t)warp * 2 * kKnnMmaEnt * 32 + lane;
+    unsigned char* qtile_ = smem + kKnnMmaOffQTile + (size_t)warp * 2 * kKnnMmaEnt * 32 + lane;
+    const int hi = lane >> 4, rot = lane & 15;
+    float qx[2], qy[2], qz[2];
+    bool valid[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int qi = qbase + 16 * t + g + 8 * j;
+      valid[j] = qi < a.m;
+      const int qs = valid[j] ? qi : 0;
+      qx[j] = __ldg(qpts + (size_t)qs * 3);
+      qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
+      qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
+    }
+    int ne[2] = {0, 0};  // queued entries per query (kKnnMmaEnt + 1 = overflow)
+    {
+      // the upper half-warp loads the {z,n} half of a pair first (every LDS.128 of the warp touches every bank once)
+      // and runs the same FMA chain on swapped operands: coefficients (cA1, cA2, cB1, cB2) = (ax, ay, az, 1) or
+      // (az, 1, ax, ay)
+      float2 cA1[2], cA2[2], cB1[2], cB2[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const float ax = -2.0f * qx[j], ay = -2.0f * qy[j], az = -2.0f * qz[j];
+        cA1[j] = hi ? make_float2(az, az) : make_float2(ax, ax);
+        cA2[j] = hi ? make_float2(1.0f, 1.0f) : make_float2(ay, ay);
+        cB1[j] = hi ? make_float2(ax, ax) : make_float2(az, az);
+        cB2[j] = hi ? make_float2(ay, ay) : make_float2(1.0f, 1.0f);
+      }
+      uint32_t w0[2] = {valid[0] ? w0a : 0u, valid[1] ? w0b : 0u}, w1[2] = {valid[0] ? w1a : 0u, valid[1] ? w1b : 0u};
+      const float thq[2] = {thqa, thqb};
+      const float4* tbase = tgt + hi;          // first load of a pair: {x,y} half (lower lanes) or {z,n} half (upper)
+      const float4* tbase2 = tgt + (hi ^ 1);
+      const int ro = 2 * rot;
+      while (__any_sync(0xffffffffu, (w0[0] | w1[0] | w0[1] | w1[1]) != 0u)) {
+        int tile[2];
+        bool act[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          act[j] = true;
+          tile[j] = 0;
+          if (w0[j]) {
+            const int p = __ffs(w0[j]) - 1;
+            w0[j] &= w0[j] - 1;
+            tile[j] = 4 * (p & 15) + (p >> 4);
+          } else if (w1[j]) {
+            const int p = __ffs(w1[j]) - 1;
+            w1[j] &= w1[j] - 1;
+            tile[j] = 4 * (p & 15) + 2 + (p >> 4);
+          } else {
+            act[j] = false;
+          }
+          act[j] = act[j] && tile[j] < ntile && ne[j] <= kKnnMmaEnt;
+        }
+        const float4* pa0 = tbase + tile[0] * T;
+        const float4* pb0 = tbase2 + tile[0] * T;
+        const float4* pa1 = tbase + tile[1] * T;
+        const float4* pb1 = tbase2 + tile[1] * T;
+        uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+        for (int i = 0; i < T / 2; i++) {
+          const int o = (2 * i + ro) & (T - 2);  // pair (i + rot) mod 16, in float4 units
+          const float4 A0 = pa0[o], B0 = pb0[o], A1 = pa1[o], B1 = pb1[o];
+          float2 f0 = ffma2(cB2[0], make_float2(B0.z, B0.w), make_float2(0.0f, 0.0f));
+          float2 f1 = ffma2(cB2[1], make_float2(B1.z, B1.w), make_float2(0.0f, 0.0f));
+          f0 = ffma2(cB1[0], make_float2(B0.x, B0.y), f0);
+          f1 = ffma2(cB1[1], make_float2(B1.x, B1.y), f1);
+          f0 = ffma2(cA2[0], make_float2(A0.z, A0.w), f0);
+          f1 = ffma2(cA2[1], make_float2(A1.z, A1.w), f1);
+          f0 = ffma2(cA1[0], make_float2(A0.x, A0.y), f0);
+          f1 = ffma2(cA1[1], make_float2(A1.x, A1.y), f1);
+          // NaN filter value / threshold counts as a candidate
+          m0 |= (!(f0.x > thq[0]) ? (1u << (2 * i)) : 0u) | (!(f0.y > thq[0]) ? (2u << (2 * i)) : 0u);
+          m1 |= (!(f1.x > thq[1]) ? (1u << (2 * i)) : 0u) | (!(f1.y > thq[1]) ? (2u << (2 * i)) : 0u);
+        }
+        // walk position i holds pair (i + rot) mod 16: rotate the word back
+        m0 = __funnelshift_l(m0, m0, ro);
+        m1 = __funnelshift_l(m1, m1, ro);
+        if (act[0] && m0) {
+          if (ne[0] < kKnnMmaEnt) {
+            qmask[ne[0] * 32] = m0;
+            qtile_[ne[0] * 32] = (unsigned char)tile[0];
+          }
+          ne[0]++;
+        }
+        if (act[1] && m1) {
+          if (ne[1] < kKnnMmaEnt) {
+            qmask[(kKnnMmaEnt + ne[1]) * 32] = m1;
+            qtile_[(kKnnMmaEnt + ne[1]) * 32] = (unsigned char)tile[1];
+          }
+          ne[1]++;
+        }
+      }
+    }
+    // ---- drain, one query at a time: exact distances of the queued candidates -> sorted (k+1)-list ----
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+      if (!valid[j]) continue;
+      const int lq = 16 * t + g + 8 * j;
+      const int qi = qbase + lq;
+      if (ne[j] > kKnnMmaEnt) {  // more tiles with candidates than the queue holds: exact warp path below
+        const int slot = atomicAdd(flag_cnt, 1);
+        flag_q[slot] = warp * kMmaQW + lq;
+        flag_vk[slot] = kNaN;  // v_k unknown: the warp path computes it
+        continue;
+      }
+      // A NaN distance at a position < k is "selected" by the reference: only the replay reproduces that.
+      bool rp = false;
+      if (need_idx)
+        for (int i = 0; i < k; i++) {
+          const float d = sqdist<GA_MODE_CPU_EXACT>(__ldg(pts + (size_t)i * 3), __ldg(pts + (size_t)i * 3 + 1),
+                                                    __ldg(pts + (size_t)i * 3 + 2), qx[j], qy[j], qz[j]);
+          rp |= d != d;
+        }
+      float TLv[KL];
+      int TLi[KL];
+#pragma unroll
+      for (int s = 0; s < KL; s++) {
+        TLv[s] = kInf;
+        TLi[s] = -1;
+      }
+      const uint32_t* em = qmask + j * kKnnMmaEnt * 32;
+      const unsigned char* et = qtile_ + j * kKnnMmaEnt * 32;
+      for (int e = 0; e < ne[j]; e++) {
+        uint32_t m = em[e * 32];
+        const int gb = (int)et[e * 32] * T;
+        while (m) {
+          const int gl = gb + __ffs(m) - 1;
+          m &= m - 1;
+          if (gl >= n) continue;  // padding can only get here when the threshold is not finite
+          const float* pu = reinterpret_cast<const float*>(tgt + 2 * (gl >> 1));
+          const int h = gl & 1;
+          const float d = sqdist<GA_MODE_CPU_EXACT>(pu[h], pu[2 + h], pu[4 + h], qx[j], qy[j], qz[j]);
+          if (d == d) list_insert<KL>(TLv, TLi, d, gl);  // NaN is never selected beyond position k
+        }
+      }
+      // ---- output / tie detection (as knn_kernel) ----
+      float vk = kInf;
+#pragma unroll
+      for (int s = 0; s < KL; s++) {
+        if (s == k - 1) {
+          vk = TLv[s];
+          rp |= TLi[s] < 0;  // fewer than k finite distances
+        }
+        if (s + 1 < KL && s < k) rp |= (TLv[s] == TLv[s + 1]) && TLi[s + 1] >= 0;
+      }
+      if (need_idx && rp) {
+        const int slot = atomicAdd(flag_cnt, 1);
+        flag_q[slot] = warp * kMmaQW + lq;
+        flag_vk[slot] = TLi[0] < 0 ? kInf : vk;
+        continue;
+      }
+      float* vo = a.val + ((size_t)batch * a.m + qi) * kout;
+      int* io = need_idx ? a.idx + ((size_t)batch * a.m + qi) * kout : nullptr;
+#pragma unroll
+      for (int s = 0; s < KL; s++) {
+        if (s >= a.skip && s < k) {
+          vo[s - a.skip] = a.do_sqrt ? __fsqrt_rn(TLv[s]) : TLv[s];
+          if (need_idx) io[s - a.skip] = TLi[s];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- flagged queries, one warp each: exact v_k if needed, then the replay ----
+  const int nflag = *flag_cnt;
+  float* cv = reinterpret_cast<float*>(scratch + (size_t)warp * 3 * KL * 8);
+  int* ci = reinterpret_cast<int*>(cv + 3 * KL);
+  for (int f = warp; f < nflag; f += kKnnMmaWarps) {
+    const int qi = qtile * kKnnMmaQT + flag_q[f];
+    const float x = __ldg(qpts + (size_t)qi * 3), y = __ldg(qpts + (size_t)qi * 3 + 1),
+                z = __ldg(qpts + (size_t)qi * 3 + 2);
+    float vk = flag_vk[f];
+    if (vk != vk) vk = kth_smallest_warp(pts, n, x, y, z, k, lane);
+    selection_replay(pts, n, x, y, z, k, vk, cv, ci, lane);
+    write_replayed(cv, ci, k, a.skip, a.do_sqrt, a.val + ((size_t)batch * a.m + qi) * kout,
+                   need_idx ? a.idx + ((size_t)batch * a.m + qi) * kout : nullptr, lane);
+  }
+}
+
+static int launch_knn_mma(const KnnArgs& a0, cudaStream_t st) {
+  KnnArgs a = a0;
+  a.qtiles = (a.m + kKnnMmaQT - 1) / kKnnMmaQT;
+  const long long ctas = (long long)a.b * a.qtiles;
+  if (ctas > 0x7fffffffLL) {
+    set_error("ga_knn: problem too large for one launch");
+    return GA_ERR_UNSUPPORTED;
+  }
+  GA_CUDA_TRY(cudaFuncSetAttribute(knn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKnnMmaSmem));
+  knn_mma_kernel<<<(unsigned)ctas, kKnnMmaThreads, kKnnMmaSmem, st>>>(a);
+  GA_LAUNCH_CHECK("knn_mma_kernel");
+  return GA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Generic k (k > 32): one warp per query, exact v_k then the replay.  O(k n) per
 // query; rare path (tf_grouping.py's own self-test uses k = 64).
 // ---------------------------------------------------------------------------
@@ -502,6 +883,11 @@ static int knn_dispatch(const KnnArgs& a, cudaStream_t st) {
     if (a.n <= 2048) {  // single chunk: lists live only while a query slot is drained
       if (kl <= 12) {
         int variant = g_knn_variant;
+        // tensor-core scans (opt-in, variant 6; data sets of at least 4 MMA blocks): bit-exact, but at config 5 it
+        // takes 2.18 ms against 1.11 ms for the fp32-filter kernel -- 40 K warp instructions per 64 queries (two MMA
+        // scans 8 K, tile walk 9 K, drain 10 K, setup) at 35 % issue utilisation with one 16-warp CTA per SM
+        // (profiles/r02_knnmma_ncu_summary.txt), where the fp32 kernel needs 34 K at twice the occupancy
+        if (variant == 6 && a.n >= 512) return launch_knn_mma(a, st);
         // large batches: 256-thread CTAs (fewer, fuller CTAs; 8 % faster at B=500); otherwise 128
         if (variant == 0 && (long long)a.b * a.m >= 148LL * 4 * 512) variant = 3;
         switch (variant) {

@@ -141,3 +141,71 @@ def test_group_point(ga, oracle):
     for b in range(3):
         np.add.at(cnt[b], idx[b].reshape(-1), 1.0)
     np.testing.assert_allclose(p.grad.cpu().numpy(), np.repeat(cnt[..., None], 7, axis=2), rtol=1e-6)
+
+
+# ---- knn_mma_kernel (tensor-core scans; default for large batches, forced here with tuning key 1 = 6) ----
+@pytest.fixture
+def knn_mma(ga):
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    lib.ga_set_tuning(1, 6)
+    yield
+    lib.ga_set_tuning(1, 0)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 8, 11])
+@pytest.mark.parametrize("shape", [(2, 512, 128), (1, 2048, 300), (2, 2048, 2048), (1, 1000, 1100), (3, 513, 64), (1, 1537, 70)])
+def test_knn_mma_bit_exact(ga, oracle, knn_mma, k, shape):
+    b, n, m = shape
+    check_knn(ga, oracle, k, cloud(800 + n, (b, n, 3)), cloud(900 + m, (b, m, 3)))
+
+
+def test_knn_mma_self_query_and_dists(ga, oracle, knn_mma):
+    pc = cloud(4, (3, 2048, 3))
+    check_knn(ga, oracle, 11, pc, pc)
+    check_knn(ga, oracle, 9, pc, pc)
+    got = ga.knn_dists(t(pc), 10).cpu().numpy()
+    assert bits_equal(got, oracle.knn_dists(pc, 10))
+
+
+@pytest.mark.parametrize("k", [1, 3, 11])
+def test_knn_mma_ties_duplicates_and_non_finite(ga, oracle, knn_mma, k):
+    rng = np.random.default_rng(k)
+    data = (rng.integers(0, 3, (2, 700, 3)).astype(np.float32) * np.float32(0.5))   # grid: ties everywhere
+    qry = (rng.integers(0, 3, (2, 90, 3)).astype(np.float32) * np.float32(0.5))
+    check_knn(ga, oracle, k, data, qry)
+    pc = cloud(5, (1, 1200, 3))
+    pc[0, 600:] = pc[0, :600]          # every point duplicated once
+    check_knn(ga, oracle, k, pc, pc)
+    z = np.zeros((1, 512, 3), np.float32)
+    check_knn(ga, oracle, k, z, z)     # all distances equal
+    data, qry = cloud(11, (1, 800, 3)), cloud(12, (1, 50, 3))
+    data[0, 150, 1] = np.nan
+    data[0, 160, 0] = np.inf
+    check_knn(ga, oracle, k, data, qry)
+    data[0, 0, 2] = np.nan             # NaN inside the first k positions
+    check_knn(ga, oracle, k, data, qry)
+    qry[0, 7, 0] = np.nan
+    check_knn(ga, oracle, k, data, qry)
+
+
+def test_knn_mma_dynamic_range_and_clusters(ga, oracle, knn_mma):
+    """Far from the origin the window covers every tile (exact path); tight clusters fill the queues."""
+    pc = cloud(21, (1, 1024, 3)) + np.float32(100.0)
+    check_knn(ga, oracle, 11, pc, pc)
+    rng = np.random.default_rng(22)
+    cl = (rng.normal(0, 1e-3, (1, 2048, 3)) + rng.integers(0, 4, (1, 2048, 1))).astype(np.float32)
+    check_knn(ga, oracle, 11, cl, cl)
+    check_knn(ga, oracle, 11, cloud(23, (1, 2048, 3), -1e-3, 1e-3), cloud(24, (1, 64, 3), -1e-3, 1e-3))
+
+
+def test_knn_mma_equals_fp32_kernel_at_full_size(ga, knn_mma):
+    """B=500 (config 5): the tensor-core kernel against the fp32-filter kernel, distances and indices."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    pc = t(cloud(4, (64, 2048, 3)))
+    v6, i6 = ga.knn_point(11, pc, pc)
+    lib.ga_set_tuning(1, 3)
+    v3, i3 = ga.knn_point(11, pc, pc)
+    lib.ga_set_tuning(1, 6)
+    assert torch.equal(v6, v3) and torch.equal(i6, i3)
