@@ -545,10 +545,210 @@ __global__ void __launch_bounds__(kBwd2Threads) nn_bwd2_kernel(const BwdArgs a) 
   }
 }
 
+// ---- third formulation (default for grids of at most one CTA per SM): one global round trip, one pass over the contributors ------------
+// nn_bwd2_kernel is a chain of five phases, four of which begin with a global load (partner xyz, index rows,
+// upstream gradients, own points): at B = 50 the kernel is that latency chain (13.6 us against a 3.9 us launch
+// floor, long-scoreboard the top stall).  Here every global load a thread needs is issued before the first
+// barrier, and the inverse index map is not a compacted list (count -> scan -> place: two passes over the
+// partner's index row and three barriers) but a table of fixed buckets: contributor e of output point p goes to
+// bucket[p][atomicAdd(cnt[p])] (16 entries of 16 bit; lists have one entry on average and, for distinct points, at
+// most the kissing number 12).  The owner of an output
+// point walks its bucket in ascending source index (selection of the next larger entry: the summation order of
+// NnDistanceGradOp, tf_nndistance.cpp:126-163, whatever order the atomics produced); a point with more than 16
+// contributors (collapsed clouds) scans the staged copy of the partner's index row, which is ascending by
+// construction.  Two barriers; 58 KB of shared memory at 2048 points and 512 keys.
+constexpr int kBwd3Threads = 256;
+constexpr int kBwd3Bucket = 16;
+
+// smem: pcloud[L] float4 | cnt[K] i32 | bucket[K][16] u16 | keys[L] i32
+static size_t bwd3_smem_bytes(int keys, int lpad) {
+  return (size_t)lpad * 16 + (size_t)keys * 4 + (size_t)keys * kBwd3Bucket * 2 + (size_t)lpad * 4;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBwd3Threads) nn_bwd3_kernel(const BwdArgs a) {
+  constexpr int T = kBwd3Threads, PER = K / T, EB = 8;  // EB: partner elements per thread and batch
+  static_assert(K % T == 0, "whole keys per thread");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lpad = ((a.n > a.m ? a.n : a.m) + 3) & ~3;
+  float4* pcloud = reinterpret_cast<float4*>(smem_raw);                       // [lpad] {x, y, z, grad_dist}
+  int* cnt = reinterpret_cast<int*>(pcloud + lpad);                           // [K]
+  unsigned short* bucket = reinterpret_cast<unsigned short*>(cnt + K);        // [K][16]
+  int* keys = reinterpret_cast<int*>(bucket + K * kBwd3Bucket);               // [lpad] the partner's index row
+
+  const int tid = threadIdx.x;
+  const int part = blockIdx.x % a.nparts;
+  const int batch = (blockIdx.x / a.nparts) >> 1;
+  const int side = (blockIdx.x / a.nparts) & 1;
+  const int P = side ? a.m : a.n;
+  const int L = side ? a.n : a.m;
+  const float* own = (side ? a.xyz2 : a.xyz1) + (size_t)batch * P * 3;
+  const float* oth = (side ? a.xyz1 : a.xyz2) + (size_t)batch * L * 3;
+  const float* own_gd = (side ? a.gd2 : a.gd1) + (size_t)batch * P;
+  const int* own_idx = (side ? a.idx2 : a.idx1) + (size_t)batch * P;
+  const float* oth_gd = (side ? a.gd1 : a.gd2) + (size_t)batch * L;
+  const int* oth_idx = (side ? a.idx1 : a.idx2) + (size_t)batch * L;
+  float* out = (side ? a.gxyz2 : a.gxyz1) + (size_t)batch * P * 3;
+
+  // Behind an arbitrary kernel (two-call form) nothing is read before the grid dependency resolves; behind the
+  // library's own forward search (one-call entry, a.ticket != nullptr) the coordinates may be read at once, the
+  // index rows once the batch element's completion ticket is in, the upstream gradients when they are final.
+  const bool twocall = a.ticket == nullptr;
+  if (twocall) asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  for (int k0 = part * K; k0 < P; k0 += a.nparts * K) {  // one round unless the cloud has more than nparts * K points
+    const int kn = min(K, P - k0);
+    // partner coordinates: global -> shared memory without passing through registers
+    for (int e = tid; e < L; e += T) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(pcloud + e);
+      const float* srcp = oth + (size_t)e * 3;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.ca.shared.global [%0+4], [%1+4], 4;\n\t"
+                   "cp.async.ca.shared.global [%0+8], [%1+8], 4;" ::"r"(dst), "l"(srcp) : "memory");
+    }
+    // ---- own points of this thread: coordinates now, index / gradient when allowed ----
+    float ox[PER], oy[PER], oz[PER], gown[PER];
+    int j2[PER];
+    bool ok[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      const int k = tid + i * T;
+      ok[i] = k < kn;
+      const int p = k0 + (ok[i] ? k : 0);
+      ox[i] = __ldg(own + (size_t)p * 3);
+      oy[i] = __ldg(own + (size_t)p * 3 + 1);
+      oz[i] = __ldg(own + (size_t)p * 3 + 2);
+    }
+    for (int i = tid; i < K; i += T) cnt[i] = 0;
+    if (!twocall) {
+      // one-call entry: index rows behind the completion ticket (or the grid dependency), gradients when final
+      __shared__ int early_flag;
+      if (tid == 0) {
+        int early = 0;
+        const volatile unsigned long long* slot = a.ticket + ticket_slot(a.call_id, batch);
+        const unsigned long long want = (a.call_id << 16) | (unsigned long long)a.expected;
+        for (int spin = 0; spin < 400 && !early; spin++) {
+          if (*slot == want) early = 1;
+          else __nanosleep(100);
+        }
+        if (early) __threadfence();  // acquire side: the stores behind the ticket are visible below
+        early_flag = early;
+        if (a.ticket_debug) {
+          unsigned long long* dbg = const_cast<unsigned long long*>(a.ticket) + kTicketSlots;
+          if (early) atomicAdd(dbg + 0, 1ull);
+          atomicAdd(dbg + 1, 1ull);
+          atomicMax(dbg + 5, global_ns());
+          if (blockIdx.x == 0) dbg[6] = global_ns();
+        }
+      }
+      __syncthreads();
+      if (!(early_flag != 0 && a.gd_final)) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    // upstream gradients of the partner -> pcloud[].w, first batch of its index row -> registers
+    for (int e = tid; e < L; e += T) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(pcloud + e) + 12;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(oth_gd + e) : "memory");
+    }
+    int pk[EB];
+#pragma unroll
+    for (int u = 0; u < EB; u++) {
+      const int e = tid + u * T;
+      pk[u] = *reinterpret_cast<const volatile int*>(oth_idx + (e < L ? e : 0));  // written by the forward grid
+    }
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      const int p = k0 + (ok[i] ? tid + i * T : 0);
+      j2[i] = *reinterpret_cast<const volatile int*>(own_idx + p);
+      gown[i] = own_gd[p];
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // cnt[] is zero, pcloud[] complete
+    for (int e0 = tid; e0 < L; e0 += EB * T) {
+      if (e0 != tid) {
+#pragma unroll
+        for (int u = 0; u < EB; u++) {
+          const int e = e0 + u * T;
+          pk[u] = *reinterpret_cast<const volatile int*>(oth_idx + (e < L ? e : 0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EB; u++) {
+        const int e = e0 + u * T;
+        const int kk = pk[u] - k0;
+        if (e < L) keys[e] = pk[u];
+        if (e < L && kk >= 0 && kk < kn) {
+          const int pos = atomicAdd(&cnt[kk], 1);
+          if (pos < kBwd3Bucket) bucket[kk * kBwd3Bucket + pos] = (unsigned short)e;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- one thread per output point ----
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      if (!ok[i]) continue;
+      const int k = tid + i * T;
+      const int cn = cnt[k];
+      float dx = 0.f, dy = 0.f, dz = 0.f;
+      if (j2[i] >= 0 && j2[i] < L) {  // direct term (own loop of the reference)
+        const float4 t4 = pcloud[j2[i]];
+        const float g = __fmul_rn(gown[i], 2.0f);
+        dx = __fmul_rn(g, __fsub_rn(ox[i], t4.x));
+        dy = __fmul_rn(g, __fsub_rn(oy[i], t4.y));
+        dz = __fmul_rn(g, __fsub_rn(oz[i], t4.z));
+      }
+      float ax = 0.f, ay = 0.f, az = 0.f;
+      if (side == 0) {  // loop 1 (direct) runs before loop 2 (scatter) for cloud 1
+        ax = __fadd_rn(ax, dx);
+        ay = __fadd_rn(ay, dy);
+        az = __fadd_rn(az, dz);
+      }
+      auto sub = [&](int e) {
+        const float4 t4 = pcloud[e];
+        const float g = __fmul_rn(t4.w, 2.0f);
+        ax = __fsub_rn(ax, __fmul_rn(g, __fsub_rn(t4.x, ox[i])));
+        ay = __fsub_rn(ay, __fmul_rn(g, __fsub_rn(t4.y, oy[i])));
+        az = __fsub_rn(az, __fmul_rn(g, __fsub_rn(t4.z, oz[i])));
+      };
+      if (cn <= kBwd3Bucket) {
+        if (cn > 0) {
+          const uint4 bw = *reinterpret_cast<const uint4*>(bucket + k * kBwd3Bucket);
+          const uint4 bv = *reinterpret_cast<const uint4*>(bucket + k * kBwd3Bucket + 8);
+          const uint32_t w[8] = {bw.x, bw.y, bw.z, bw.w, bv.x, bv.y, bv.z, bv.w};
+          int prev = -1;
+          for (int r = 0; r < cn; r++) {  // next larger source index
+            int best = 0x10000;
+#pragma unroll
+            for (int q = 0; q < kBwd3Bucket; q++) {
+              const int v = (int)((w[q >> 1] >> (16 * (q & 1))) & 0xffffu);
+              if (q < cn && v > prev && v < best) best = v;
+            }
+            sub(best);
+            prev = best;
+          }
+        }
+      } else {
+        const int want = k0 + k;
+        for (int e = 0; e < L; e++)
+          if (keys[e] == want) sub(e);
+      }
+      if (side == 1) {  // for cloud 2 the scatter of loop 1 comes first, its own loop 2 last
+        ax = __fadd_rn(ax, dx);
+        ay = __fadd_rn(ay, dy);
+        az = __fadd_rn(az, dz);
+      }
+      const int p = k0 + k;
+      out[(size_t)p * 3] = ax;
+      out[(size_t)p * 3 + 1] = ay;
+      out[(size_t)p * 3 + 2] = az;
+    }
+    __syncthreads();  // a further round reuses cnt / bucket / pcloud
+  }
+}
+
 extern int g_tickets;                    // nn_distance_fwd_mma.cu
 extern thread_local int t_want_tickets;  // nn_distance_fwd_mma.cu
 int g_pdl = 1;         // tuning hook (key 15): 0 = plain launches (no programmatic dependent launch)
-int g_bwd_kernel = 0;  // tuning hook (key 14): 0 auto (second formulation when it applies), 1 = stable counting sort
+int g_bwd_kernel = 0;  // tuning hook (key 14): 0 auto, 1 = stable counting sort, 2 = second formulation (compacted lists), 3 = third (buckets, one round trip)
 int g_bwd_stage = 1;   // tuning hook (key 13): 0 = gather the partner cloud from global memory (no staging)
 int g_bwd_split = -1;  // tuning hook (key 9): -1 auto, 0 one CTA per cloud, 1 output points split over 4 CTAs
 
@@ -636,6 +836,43 @@ extern "C" int ga_nn_distance_bwd(int b, int n, int m, const float* xyz1, const 
     }
     const unsigned grid = (unsigned)(2 * b * parts);
     const int lpad = (lmax + 3) & ~3;  // keeps the float4 array behind the int array 16-byte aligned
+    // One CTA per SM or fewer: the kernel is its chain of global round trips, and nn_bwd3_kernel has one instead of
+    // four (B = 1: 10.2 vs 12.2 us, B = 10: 10.1 vs 12.2 us).  Larger grids are throughput-bound and the compacted
+    // lists of nn_bwd2_kernel cost fewer instructions and less shared memory per CTA (B = 50: 14.3 vs 16.3 us,
+    // B = 512: 51 vs 65 us, B = 4096: 293 vs 436 us; profiles/r02_tune_bwd.txt).
+    if (g_bwd_kernel == 3 || (g_bwd_kernel == 0 && (long long)grid <= (long long)sm_count())) {
+      static std::atomic<unsigned> done3{0};
+      if (!(done3.load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+        GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd3_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bwd3_smem_bytes(2048, kBwdStageMax)));
+        GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd3_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bwd3_smem_bytes(1024, kBwdStageMax)));
+        GA_CUDA_TRY(cudaFuncSetAttribute(nn_bwd3_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bwd3_smem_bytes(512, kBwdStageMax)));
+        done3.fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+      }
+      cudaLaunchConfig_t cfg3 = {};
+      cfg3.gridDim = dim3(grid);
+      cfg3.blockDim = dim3(kBwd3Threads);
+      cfg3.stream = st;
+      cudaLaunchAttribute attr3[1];
+      attr3[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr3[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg3.attrs = attr3;
+      cfg3.numAttrs = g_pdl ? 1 : 0;
+      if (per <= 512) {
+        cfg3.dynamicSmemBytes = bwd3_smem_bytes(512, lpad);
+        GA_CUDA_TRY(cudaLaunchKernelEx(&cfg3, nn_bwd3_kernel<512>, a));
+      } else if (per <= 1024) {
+        cfg3.dynamicSmemBytes = bwd3_smem_bytes(1024, lpad);
+        GA_CUDA_TRY(cudaLaunchKernelEx(&cfg3, nn_bwd3_kernel<1024>, a));
+      } else {
+        cfg3.dynamicSmemBytes = bwd3_smem_bytes(2048, lpad);
+        GA_CUDA_TRY(cudaLaunchKernelEx(&cfg3, nn_bwd3_kernel<2048>, a));
+      }
+      GA_LAUNCH_CHECK("nn_bwd3_kernel");
+      return GA_OK;
+    }
     // Programmatic dependent launch: the grid may start while the preceding kernel of the stream (the
     // forward search, which triggers early) drains, and blocks in griddepcontrol.wait before it reads
     // anything that kernel wrote.  After a kernel that never triggers this is an ordinary launch.

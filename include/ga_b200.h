@@ -207,7 +207,7 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  *    6 split kernel queries/thread  7 HMMA grid config (0 = 5)  8 persistent grids' CTA count (0 = SMs)
  *    9 gradient CTAs per cloud (-1 auto, 0 one, 1 four, 2 two)  10 host graph replay (0 auto, 1 off, 2 at once)
  *   11 replay chunks (0 auto)      12 tcgen05 grid CTAs (0 = SMs)  13 first gradient kernel: stage partner (1)
- *   14 gradient kernel (0 auto = atomics + list sort, 1 = stable counting sort)   15 dependent launch (1)
+ *   14 gradient kernel (0 auto, 1 = stable counting sort, 2 = compacted lists, 3 = buckets + one round trip)   15 dependent launch (1)
  *   16 all-pairs kernel (0 auto = tensor-core scan, 1 = fp32 filter)   17 replay: dist/idx mirrored to the host
  *      (0 auto, 1 never, 2 always)   18 completion tickets (0 never, 1 one-call entry only, 2 always + debug, 3 always)
  *   19 all-pairs source clouds per CTA (0 auto)   20 tcgen05 kernel, development build: bit 0 no refine, bit 1 no
