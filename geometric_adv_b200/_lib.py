@@ -39,6 +39,7 @@ SIGNATURES = {
     "ga_nn_distance_bwd_host": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ga_nn_distance_fwd_bwd_host": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i]),
     "ga_chamfer_per_cloud": (_i, [_i, _i, _i, _p, _p, _p, _p]),
+    "ga_chamfer_loss_terms": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
     "ga_chamfer_all_pairs": (_i, [_i, _i, _p, _i, _i, _p, _i, _p]),
     "ga_chamfer_all_pairs_directed": (_i, [_i, _i, _p, _i, _i, _p, _i, _p]),
     "ga_symmetrize_rows": (_i, [_i, _i, _i, _p, _p, _p]),

@@ -23,6 +23,12 @@ Deliberate, documented differences:
   creates them once per class and never resets them (adv_ae.py:152 vs :214), which makes
   a batch depend on all batches before it; resetting makes pairs independent, so that pairs
   can be sharded over GPUs with bit-identical results.  ``reset_adam=False`` restores the quirk.
+* single_forward=True (default): the reference evaluates the six loss vectors in a second sess.run AFTER the update
+  (adv_ae.py:219-221), i.e. a second AE forward and two more Chamfer searches per iteration.  Those values are exactly
+  what the forward pass of the NEXT iteration computes (same perturbation, same frozen network), so the iteration
+  here is forward -> best-so-far bookkeeping for the previous update -> backward -> Adam, plus one closing forward
+  after the last update: same metrics for every update, one AE forward and two searches per iteration instead of
+  two and four.  single_forward=False keeps the reference's order of evaluation (tests compare the two).
 * Update rule follows TensorFlow's Adam (epsilon outside the bias correction:
   lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps)), not torch.optim.Adam.
 """
@@ -58,8 +64,12 @@ class PointNetAE(nn.Module):
         return self.decoder(z).view(-1, self.n_points, 3), z
 
 
-def chamfer_per_pc(a, b):
-    """mean(d_ab,1) + mean(d_ba,1) and max(d_ab,1), as adv_ae.py:120-121,131-133 build them."""
+def chamfer_per_pc(a, b, fused=True):
+    """mean(d_ab,1) + mean(d_ba,1) and max(d_ab,1), as adv_ae.py:120-121,131-133 build them: one search and one
+    reduction launch (ops.chamfer_loss_terms); fused=False builds them from nn_distance with torch reductions."""
+    if fused and a.is_cuda:
+        cd, mx, _, _ = ops.chamfer_loss_terms(a, b)
+        return cd, mx
     d1, _, d2, _ = ops.nn_distance(a, b)
     return d1.mean(dim=1) + d2.mean(dim=1), d1.amax(dim=1)
 
@@ -69,7 +79,8 @@ class GeometricAttack:
     loss_dist_type=chamfer, dist_weight 1.0) for one batch of (source, target) pairs."""
 
     def __init__(self, ae, batch_size, n_points=2048, lr=0.01, dist_weight=1.0, num_iterations=500,
-                 num_iterations_thresh=400, use_cuda_graph=True, reset_adam=True, device="cuda"):
+                 num_iterations_thresh=400, use_cuda_graph=True, reset_adam=True, device="cuda", single_forward=True,
+                 fused_loss=True):
         self.ae = ae.to(device).eval()  # is_training(False): BatchNorm frozen (adv_ae.py:210)
         for p in self.ae.parameters():
             p.requires_grad_(False)
@@ -78,6 +89,8 @@ class GeometricAttack:
         self.iters, self.thresh = num_iterations, num_iterations_thresh
         self.device = torch.device(device)
         self.reset_adam = reset_adam
+        self.single_forward = single_forward
+        self.fused_loss = fused_loss
         self.use_graph = use_cuda_graph and self.device.type == "cuda"
         f32 = dict(dtype=torch.float32, device=self.device)
         self.x = torch.zeros(batch_size, n_points, 3, **f32)        # source clouds
@@ -88,6 +101,8 @@ class GeometricAttack:
         self.v = torch.zeros_like(self.pert)
         self.t = torch.zeros((), **f32)
         self.collect = torch.zeros((), dtype=torch.bool, device=self.device)  # iteration+1 >= thresh
+        self.collect_prev = torch.zeros((), dtype=torch.bool, device=self.device)  # the same for the previous update
+        self.metrics_graph = None
         self.best_err = torch.full((batch_size,), 1e10, **f32)
         self.best_metrics = torch.zeros(batch_size, 4, **f32)       # loss_adv, loss_dist, source CD, target NRE
         self.best_adv = torch.zeros(batch_size, n_points, 3, **f32)
@@ -96,34 +111,66 @@ class GeometricAttack:
         self.graph = None
 
     # -- one iteration (adv_ae.py:217-246) ------------------------------------------------
-    def _iteration(self):
+    def _bookkeeping(self, adv, recon, err, src_cd, src_max, collect):
+        """Metrics of the current perturbation and the best-so-far update (adv_ae.py:219-246)."""
+        pert_sq = (self.pert * self.pert).sum(dim=2)
+        self.last = {"loss_adv": err, "loss_dist": src_cd, "loss_pert": pert_sq.sum(dim=1).sqrt(),
+                     "loss_max": src_max, "source_chamfer_dist": src_cd, "target_recon_error": err}
+        better = collect & (err < self.best_err)
+        self.best_err.copy_(torch.where(better, err, self.best_err))
+        met = torch.stack([err, src_cd, src_cd, err / self.ref], dim=1)
+        self.best_metrics.copy_(torch.where(better[:, None], met, self.best_metrics))
+        self.best_adv.copy_(torch.where(better[:, None, None], adv, self.best_adv))
+        self.best_recon.copy_(torch.where(better[:, None, None], recon, self.best_recon))
+
+    def _adam(self, g):
         b1, b2, eps = 0.9, 0.999, 1e-8
+        self.t += 1.0
+        self.m.mul_(b1).add_(g, alpha=1 - b1)
+        self.v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        lr_t = self.lr * torch.sqrt(1 - b2 ** self.t) / (1 - b1 ** self.t)
+        self.pert.sub_(lr_t * self.m / (self.v.sqrt() + eps))
+
+    def _iteration(self):
+        if self.single_forward:
+            return self._iteration_single()
         adv = self.x + self.pert
         recon, _ = self.ae(adv)
-        loss_adv, _ = chamfer_per_pc(recon, self.gt)
-        loss_dist, _ = chamfer_per_pc(adv, self.x)
+        loss_adv, _ = chamfer_per_pc(recon, self.gt, self.fused_loss)
+        loss_dist, _ = chamfer_per_pc(adv, self.x, self.fused_loss)
         loss = (loss_adv + self.w * loss_dist).sum()
         (g,) = torch.autograd.grad(loss, self.pert)
         with torch.no_grad():
-            self.t += 1.0
-            self.m.mul_(b1).add_(g, alpha=1 - b1)
-            self.v.mul_(b2).addcmul_(g, g, value=1 - b2)
-            lr_t = self.lr * torch.sqrt(1 - b2 ** self.t) / (1 - b1 ** self.t)
-            self.pert.sub_(lr_t * self.m / (self.v.sqrt() + eps))
+            self._adam(g)
             # second sess.run: metrics at the UPDATED perturbation
             adv = self.x + self.pert
             recon, _ = self.ae(adv)
-            err, _ = chamfer_per_pc(recon, self.gt)            # loss_ae_per_pc == loss_adv
-            src_cd, src_max = chamfer_per_pc(adv, self.x)      # input_dist_per_pc, max_dist_per_pc
-            pert_sq = (self.pert * self.pert).sum(dim=2)
-            self.last = {"loss_adv": err, "loss_dist": src_cd, "loss_pert": pert_sq.sum(dim=1).sqrt(),
-                         "loss_max": src_max, "source_chamfer_dist": src_cd, "target_recon_error": err}
-            better = self.collect & (err < self.best_err)
-            self.best_err.copy_(torch.where(better, err, self.best_err))
-            met = torch.stack([err, src_cd, src_cd, err / self.ref], dim=1)
-            self.best_metrics.copy_(torch.where(better[:, None], met, self.best_metrics))
-            self.best_adv.copy_(torch.where(better[:, None, None], adv, self.best_adv))
-            self.best_recon.copy_(torch.where(better[:, None, None], recon, self.best_recon))
+            err, _ = chamfer_per_pc(recon, self.gt, self.fused_loss)            # loss_ae_per_pc == loss_adv
+            src_cd, src_max = chamfer_per_pc(adv, self.x, self.fused_loss)      # input_dist_per_pc, max_dist_per_pc
+            self._bookkeeping(adv, recon, err, src_cd, src_max, self.collect)
+
+    def _iteration_single(self):
+        """forward at the current perturbation = metrics of the PREVIOUS update (collect_prev) + loss of this one."""
+        adv = self.x + self.pert
+        recon, _ = self.ae(adv)
+        loss_adv, _ = chamfer_per_pc(recon, self.gt, self.fused_loss)
+        loss_dist, src_max = chamfer_per_pc(adv, self.x, self.fused_loss)
+        with torch.no_grad():
+            self._bookkeeping(adv.detach(), recon.detach(), loss_adv.detach(), loss_dist.detach(), src_max.detach(),
+                              self.collect_prev)
+        loss = (loss_adv + self.w * loss_dist).sum()
+        (g,) = torch.autograd.grad(loss, self.pert)
+        with torch.no_grad():
+            self._adam(g)
+
+    def _metrics_only(self):
+        """Closing forward of the single-forward mode: the metrics of the last update."""
+        with torch.no_grad():
+            adv = self.x + self.pert
+            recon, _ = self.ae(adv)
+            err, _ = chamfer_per_pc(recon, self.gt, self.fused_loss)
+            src_cd, src_max = chamfer_per_pc(adv, self.x, self.fused_loss)
+            self._bookkeeping(adv, recon, err, src_cd, src_max, self.collect_prev)
 
     def _capture(self):
         s = torch.cuda.Stream(device=self.device)
@@ -188,7 +235,11 @@ class GeometricAttack:
         self.init_pert(pair_ids=pair_ids)
         for it in range(iters):
             self.collect.fill_((it + 1) >= min(self.thresh, iters))
+            self.collect_prev.fill_(it >= 1 and it >= min(self.thresh, iters))  # update `it` is iteration it - 1
             self.step()
+        if self.single_forward:
+            self.collect_prev.fill_(iters >= 1 and iters >= min(self.thresh, iters))
+            self._metrics_only()
         metrics = torch.cat([self.best_metrics, self.best_err[:, None]], dim=1)
         return metrics.clone(), self.best_adv.clone(), self.best_recon.clone()
 

@@ -6,32 +6,49 @@ namespace ga {
 // out[i] = mean(dist1[i,:]) + mean(dist2[i,:])  (src/adv_ae.py:120-121,
 // attacker/prepare_indices_for_attack.py:113-114).  Fixed order: each thread sums a
 // strided slice in ascending order, then a fixed shuffle/smem tree.
+// max1 (optional): max(dist1[i,:]) (adv_ae.py:131-133, max_dist_per_pc); NaN if any entry is NaN, as tf.reduce_max /
+// torch.amax give.  One launch replaces the two means, the add and the max of the attack's loss graph.
 __global__ void __launch_bounds__(256) chamfer_per_cloud_kernel(int n, int m, const float* __restrict__ dist1,
                                                                const float* __restrict__ dist2,
-                                                               float* __restrict__ out) {
-  __shared__ float part[2][8];
+                                                               float* __restrict__ out, float* __restrict__ max1) {
+  __shared__ float part[3][8];
+  __shared__ int anynan[8];
   const int i = blockIdx.x, tid = threadIdx.x;
-  float s1 = 0.f, s2 = 0.f;
-  for (int j = tid; j < n; j += 256) s1 += dist1[(size_t)i * n + j];
+  float s1 = 0.f, s2 = 0.f, mx = -__int_as_float(0x7f800000);
+  int nan = 0;
+  for (int j = tid; j < n; j += 256) {
+    const float v = dist1[(size_t)i * n + j];
+    s1 += v;
+    mx = fmaxf(mx, v);
+    nan |= v != v;
+  }
   for (int j = tid; j < m; j += 256) s2 += dist2[(size_t)i * m + j];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    nan |= __shfl_xor_sync(0xffffffffu, nan, o);
   }
   if ((tid & 31) == 0) {
     part[0][tid >> 5] = s1;
     part[1][tid >> 5] = s2;
+    part[2][tid >> 5] = mx;
+    anynan[tid >> 5] = nan;
   }
   __syncthreads();
   if (tid == 0) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, c = part[2][0];
+    int nn = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
       a += part[0][w];
       b += part[1][w];
+      c = fmaxf(c, part[2][w]);
+      nn |= anynan[w];
     }
     out[i] = a / (float)n + b / (float)m;
+    if (max1 != nullptr) max1[i] = nn ? __int_as_float(0x7fc00000) : c;
   }
 }
 
@@ -45,7 +62,20 @@ extern "C" int ga_chamfer_per_cloud(int b, int n, int m, const float* dist1, con
     return GA_ERR_INVALID_ARGUMENT;
   }
   if (b == 0) return GA_OK;
-  chamfer_per_cloud_kernel<<<b, 256, 0, as_stream(stream)>>>(n, m, dist1, dist2, out);
+  chamfer_per_cloud_kernel<<<b, 256, 0, as_stream(stream)>>>(n, m, dist1, dist2, out, nullptr);
+  GA_LAUNCH_CHECK("chamfer_per_cloud_kernel");
+  return GA_OK;
+}
+
+extern "C" int ga_chamfer_loss_terms(int b, int n, int m, const float* dist1, const float* dist2, float* cd,
+                                     float* max1, ga_stream_t stream) {
+  using namespace ga;
+  if (b < 0 || n < 0 || m < 0) {
+    set_error("ga_chamfer_loss_terms: negative size");
+    return GA_ERR_INVALID_ARGUMENT;
+  }
+  if (b == 0) return GA_OK;
+  chamfer_per_cloud_kernel<<<b, 256, 0, as_stream(stream)>>>(n, m, dist1, dist2, cd, max1);
   GA_LAUNCH_CHECK("chamfer_per_cloud_kernel");
   return GA_OK;
 }

@@ -24,7 +24,7 @@ from ._lib import GA_MODE_CPU_EXACT, GA_MODE_GPU_REF
 
 __all__ = [
     "nn_distance", "nn_distance_grad", "chamfer_3DDist", "chamfer_3DFunction", "knn_point", "select_top_k",
-    "group_point", "knn_dists", "chamfer_per_cloud", "chamfer_all_pairs", "set_default_mode", "set_pruning",
+    "group_point", "knn_dists", "chamfer_per_cloud", "chamfer_loss_terms", "chamfer_all_pairs", "set_default_mode", "set_pruning",
     "launch_count",
     "GA_MODE_CPU_EXACT", "GA_MODE_GPU_REF",
 ]
@@ -275,6 +275,63 @@ def chamfer_per_cloud(dist1, dist2):
         _lib.check(lib.ga_chamfer_per_cloud(b, n, m, dist1.data_ptr(), dist2.data_ptr(), out.data_ptr(),
                                             _stream(dist1)))
     return out
+
+
+# --------------------------------------------------------------------------- fused Chamfer loss terms
+@torch.library.custom_op("geometric_adv_b200::chamfer_loss_terms", mutates_args=())
+def _chamfer_loss_terms_op(xyz1: torch.Tensor, xyz2: torch.Tensor, mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(cd, max1, idx1, idx2): the search and ONE reduction launch (ga_chamfer_loss_terms)."""
+    lib = _lib.load()
+    dist1, idx1, dist2, idx2 = _nn_distance_fwd(xyz1, xyz2, mode)
+    b, n = dist1.shape
+    m = dist2.shape[1]
+    cd = torch.empty((b,), dtype=torch.float32, device=dist1.device)
+    mx = torch.empty((b,), dtype=torch.float32, device=dist1.device)
+    if dist1.device.type != "cuda":
+        raise ValueError("chamfer_loss_terms expects CUDA tensors")
+    with _Guard(dist1.device):
+        _lib.check(lib.ga_chamfer_loss_terms(b, n, m, dist1.data_ptr(), dist2.data_ptr(), cd.data_ptr(), mx.data_ptr(),
+                                             _stream(dist1)))
+    return cd, mx, idx1, idx2
+
+
+@_chamfer_loss_terms_op.register_fake
+def _(xyz1, xyz2, mode):
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    return (xyz1.new_empty((b,)), xyz1.new_empty((b,)), xyz1.new_empty((b, n), dtype=torch.int32),
+            xyz1.new_empty((b, m), dtype=torch.int32))
+
+
+def _chamfer_loss_terms_setup(ctx, inputs, output):
+    xyz1, xyz2, _mode = inputs
+    _cd, _mx, idx1, idx2 = output
+    ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+
+
+def _chamfer_loss_terms_backward(ctx, grad_cd, grad_max, grad_idx1, grad_idx2):
+    """d cd / d dist1 = 1/N, d cd / d dist2 = 1/M, exactly what autograd derives for mean(dist1,1) + mean(dist2,1):
+    grad.unsqueeze(1).expand(...) / N.  The max term is an evaluation metric (adv_ae.py:131-133) and carries no
+    gradient, like idx."""
+    xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+    if grad_cd is None:
+        grad_cd = torch.zeros((idx1.shape[0],), dtype=torch.float32, device=idx1.device)
+    n, m = idx1.shape[1], idx2.shape[1]
+    gd1 = (grad_cd.unsqueeze(1).expand(-1, n) / n).contiguous()
+    gd2 = (grad_cd.unsqueeze(1).expand(-1, m) / m).contiguous()
+    g1, g2 = _nn_distance_grad_op(xyz1, xyz2, gd1, idx1, gd2, idx2)
+    return g1, g2, None
+
+
+_chamfer_loss_terms_op.register_autograd(_chamfer_loss_terms_backward, setup_context=_chamfer_loss_terms_setup)
+
+
+def chamfer_loss_terms(xyz1, xyz2, mode=None):
+    """The per-cloud loss terms of the attack graph from ONE search and ONE reduction launch:
+    cd = mean(dist1,1) + mean(dist2,1) (adv_ae.py:120-121; bit-equal to chamfer_per_cloud(nn_distance(...))) and
+    max1 = max(dist1,1) (:131-133).  Differentiable through cd.  Returns (cd, max1, idx1, idx2)."""
+    mode = _default_mode if mode is None else mode
+    _check_nn_distance_args(xyz1, xyz2)
+    return _chamfer_loss_terms_op(xyz1.contiguous(), xyz2.contiguous(), int(mode))
 
 
 def chamfer_all_pairs(clouds, row0=0, rows=None, mode=None, directed=False):

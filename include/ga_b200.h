@@ -136,6 +136,11 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
  * attacker/prepare_indices_for_attack.py:113-114).  Fixed summation tree => reproducible. */
 int ga_chamfer_per_cloud(int b, int n, int m, const float* dist1, const float* dist2, float* out,
                          ga_stream_t stream);
+/* The loss terms the attack graph builds from one nn_distance call (src/adv_ae.py:120-121,131-133), in one
+ * launch: cd[i] = mean(dist1[i,:]) + mean(dist2[i,:]) (same summation tree as ga_chamfer_per_cloud: same bits) and
+ * max1[i] = max(dist1[i,:]) (NaN if any entry is; max1 may be NULL). */
+int ga_chamfer_loss_terms(int b, int n, int m, const float* dist1, const float* dist2, float* cd, float* max1,
+                          ga_stream_t stream);
 
 /* All-pairs driver of attacker/prepare_indices_for_attack.py:104-139: `clouds` (s,n,3);
  * out (rows,s) with out[r, j] = CD(source = clouds[j], target = clouds[row0 + r]) as in

@@ -217,3 +217,47 @@ def test_prepare_indices_pipeline(ga, tmp_path):
             assert top[row, tc, :len(w)].tolist() == w.tolist() and np.all(top[row, tc, len(w):] == -1)
     p1, p2 = sharding.save_chamfer_nn_files(str(tmp_path), cd, slice_idx)
     assert np.array_equal(np.load(p2), nn.cpu().numpy())
+
+
+def test_chamfer_loss_terms_fused_op(ga):
+    """One search + one reduction launch: cd bit-equal to chamfer_per_cloud(nn_distance), max bit-equal to amax,
+    gradient bit-equal to autograd through nn_distance + mean."""
+    a = t(cloud(31, (6, 700, 3))).requires_grad_(True)
+    b = t(cloud(32, (6, 900, 3))).requires_grad_(True)
+    cd, mx, i1, i2 = ga.chamfer_loss_terms(a, b)
+    d1, j1, d2, j2 = ga.nn_distance(a, b)
+    assert torch.equal(i1, j1) and torch.equal(i2, j2)
+    assert torch.equal(cd, ga.chamfer_per_cloud(d1.detach(), d2.detach()))
+    assert torch.equal(mx, d1.amax(dim=1))
+    ref = d1.mean(dim=1) + d2.mean(dim=1)
+    assert torch.allclose(cd, ref, rtol=1e-6)
+    w = t(np.linspace(0.5, 2.0, 6).astype(np.float32))
+    ga1, gb1 = torch.autograd.grad((cd * w).sum(), (a, b))
+    ga2, gb2 = torch.autograd.grad((ref * w).sum(), (a, b))
+    assert torch.equal(ga1, ga2) and torch.equal(gb1, gb2)
+    nanrow = a.detach().clone()
+    nanrow[2, 5, 0] = float("nan")
+    _, mx2, _, _ = ga.chamfer_loss_terms(nanrow, b.detach())
+    assert bool(torch.isnan(mx2[2])) and not bool(torch.isnan(mx2[[0, 1, 3, 4, 5]]).any())
+
+
+def test_attack_single_forward_equals_the_reference_order():
+    """The metrics of an update are what the next iteration's forward computes: the single-forward iteration
+    (one AE forward, two searches) gives the results of the reference's order (two forwards, four searches)."""
+    from geometric_adv_b200.attack import GeometricAttack, PointNetAE
+    torch.manual_seed(0)
+    ae = PointNetAE(512)
+    src, tgt = t(cloud(1, (4, 512, 3))), t(cloud(2, (4, 512, 3)))
+    res = []
+    for single in (False, True):
+        atk = GeometricAttack(ae, 4, 512, num_iterations=14, num_iterations_thresh=9, use_cuda_graph=False,
+                              single_forward=single)
+        res.append(atk.run(src, tgt))
+    for a, b in zip(res[0], res[1]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    res2 = []
+    for fused in (False, True):
+        atk = GeometricAttack(ae, 4, 512, num_iterations=14, num_iterations_thresh=9, fused_loss=fused)
+        res2.append(atk.run(src, tgt))
+    for a, b in zip(res2[0], res2[1]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
