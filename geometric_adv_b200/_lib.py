@@ -56,6 +56,7 @@ SIGNATURES = {
     "ga_probe_launch_floor": (_i, [_i, C.POINTER(C.c_float), _p]),
     "ga_debug_mma_filter": (_i, [_i, _i, _p, _p, _p, _p]),
     "ga_debug_umma_filter": (_i, [_i, _i, _p, _p, _p, _p]),
+    "ga_debug_ws_trace": (_i, [_p]),
 }
 
 

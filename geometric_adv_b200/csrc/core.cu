@@ -32,6 +32,9 @@ extern int g_tickets;            // nn_distance_fwd_mma.cu
 extern int g_pairs_ablk;         // all_pairs.cu
 extern int g_umma_groups;        // nn_distance_fwd_umma.cu
 extern int g_umma_auto;          // nn_distance_fwd.cu
+extern int g_ws_scan;            // nn_distance_fwd_mma_ws.cu
+extern int g_ws_idle_ns;         // nn_distance_fwd_mma_ws.cu
+extern int g_ws_dev;             // nn_distance_fwd_mma_ws.cu
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -227,6 +230,18 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 21) {
     ga::g_umma_auto = value;
+    return GA_OK;
+  }
+  if (key == 22) {
+    ga::g_ws_scan = value;
+    return GA_OK;
+  }
+  if (key == 23) {
+    ga::g_ws_idle_ns = value;
+    return GA_OK;
+  }
+  if (key == 24) {
+    ga::g_ws_dev = value;
     return GA_OK;
   }
   if (key == 11) {

@@ -269,6 +269,8 @@ int launch_fwd_mma(const FwdArgs& a, int mode, cudaStream_t st);          // nn_
 int launch_fwd_mma_persist(const FwdArgs& a, int mode, cudaStream_t st);  // nn_distance_fwd_mma.cu
 int launch_fwd_mma_balanced(const FwdArgs& a, int mode, cudaStream_t st); // nn_distance_fwd_mma.cu
 int launch_fwd_umma(const FwdArgs& a, int mode, cudaStream_t st);         // nn_distance_fwd_umma.cu
+int launch_fwd_mma_ws(const FwdArgs& a, int mode, cudaStream_t st);       // nn_distance_fwd_mma_ws.cu
+bool fwd_mma_ws_supported(int b, int n, int m);                           // nn_distance_fwd_mma_ws.cu
 bool fwd_umma_supported(int n, int m);                                    // nn_distance_fwd_umma.cu
 extern thread_local int t_want_tickets;                                   // nn_distance_fwd_mma.cu
 int g_umma_auto = 1;  // tuning hook (key 21): 0 = never pick the tcgen05 kernel automatically
@@ -360,6 +362,7 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   if (variant == 21) return launch_fwd_mma_persist(a, mode, st);
   if (variant == 22) return launch_fwd_umma(a, mode, st);
   if (variant == 23) return launch_fwd_mma_balanced(a, mode, st);
+  if (variant == 24) return launch_fwd_mma_ws(a, mode, st);
   switch (variant) {
 #define GA_FWD_CASE(ID, TH, QQ, TT, CC)                                                          \
   case ID: {                                                                                     \

@@ -207,7 +207,7 @@ int ga_split_by_threshold(int b, int n, const float* pc, const float* score, flo
 int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
 /* Tuning hooks for benchmarks and tests (process-wide; defaults in parentheses):
  *    0 forward kernel: 0 auto, 1-15 fp32-filter tile shapes, 20 HMMA grid kernel, 21 persistent HMMA,
- *      22 tcgen05/TMEM, 23 balanced persistent HMMA          1 kNN variant            2 host path (0 auto,
+ *      22 tcgen05/TMEM, 23 balanced persistent HMMA, 24 warp-specialised persistent HMMA   1 kNN variant            2 host path (0 auto,
  *      1 copies, 2 zero-copy)      3 host chunks (0 auto)     4 pruned-path variant    5 cluster split S (-1 auto)
  *    6 split kernel queries/thread  7 HMMA grid config (0 = 5)  8 persistent grids' CTA count (0 = SMs)
  *    9 gradient CTAs per cloud (-1 auto, 0 one, 1 four, 2 two)  10 host graph replay (0 auto, 1 off, 2 at once)
@@ -217,7 +217,9 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  *      (0 auto, 1 never, 2 always)   18 completion tickets (0 never, 1 one-call entry only, 2 always + debug, 3 always)
  *   19 all-pairs source clouds per CTA (0 auto)   20 tcgen05 kernel, development build: bit 0 no refine, bit 1 no
  *      drain, bit 3 no helper, bits 8.. traced CTA (0 = product build)   21 automatic choice of the tcgen05 kernel
- *      between the HMMA kernel's wave steps (1) */
+ *      between the HMMA kernel's wave steps (1)   22 variant 24: scan warps (0 = 8; 8 or 12 of 16)   23 variant 24: start
+ *      offset of every scheduler's second scan warp, ns (0)   24 variant 24, development: bit 0 no refine, bit 1 no
+ *      query loads in the scan warps (wrong results; timing only) */
 int ga_set_tuning(int key, int value);
 /* Empty-kernel launch floor in microseconds (average over `reps` launches). */
 int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);
@@ -230,6 +232,9 @@ const char* ga_last_kernel(void);
 int ga_debug_mma_filter(int n, int m, const float* xyz1, const float* xyz2, float* out, ga_stream_t stream);
 /* Same evidence for the tcgen05 / TMEM filter (forward variant 22, nn_distance_fwd_umma.cu). */
 int ga_debug_umma_filter(int n, int m, const float* xyz1, const float* xyz2, float* out, ga_stream_t stream);
+/* Development: per-warp clock totals of the following warp-specialised forward launches (variant 24) go to `buf`
+ * (device memory, grid x 16 warps x 4 int64: waiting, working, staging, total); NULL switches it off. */
+int ga_debug_ws_trace(long long* buf);
 
 #ifdef __cplusplus
 }

@@ -11,9 +11,10 @@ from util import bits_equal, cloud
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 U = 2.0 ** -24
-MMA_CFGS = [1, 2, 3, 4, 5, 21, 1021, 7021, 23, 1023, 7023, 50023]
+MMA_CFGS = [1, 2, 3, 4, 5, 21, 1021, 7021, 23, 1023, 7023, 50023, 24, 1024, 7024, 50024]
 # 21: persistent kernel (one CTA per SM), 23: balanced persistent kernel (jobs split over warps by target
-# blocks, published row keys merged); G*1000+21 / +23: the same with G CTAs
+# blocks, published row keys merged), 24: warp-specialised persistent kernel (scan warps / helper warps);
+# G*1000+21 / +23 / +24: the same with G CTAs
 
 
 def t(a):
@@ -50,7 +51,7 @@ def test_filter_values_within_documented_bound(ga, n, m, scale):
 
 
 def run_variant(ga, lib, a, b, cfg, mode=0):
-    if cfg % 1000 in (21, 23):
+    if cfg % 1000 in (21, 23, 24):
         lib.ga_set_tuning(0, cfg % 1000)
         lib.ga_set_tuning(8, cfg // 1000)
     else:
@@ -69,7 +70,7 @@ def check(ga, oracle, a, b, mode=0, cfgs=MMA_CFGS):
     lib = _lib.load()
     want = oracle.nn_distance(a, b, mode)
     for cfg in cfgs:
-        if cfg % 1000 in (21, 23) and (a.shape[1] > 2048 or b.shape[1] > 2048 or a.shape[1] == 0 or b.shape[1] == 0):
+        if cfg % 1000 in (21, 23, 24) and (a.shape[1] > 2048 or b.shape[1] > 2048 or a.shape[1] == 0 or b.shape[1] == 0):
             continue  # the persistent kernel takes clouds of at most 2048 points
         got = run_variant(ga, lib, a, b, cfg, mode)
         for nme, g, w in zip(["dist1", "idx1", "dist2", "idx2"], got, want):
@@ -91,8 +92,8 @@ def test_ragged_shapes(ga, oracle, shape):
 
 
 def test_batch_of_8(ga, oracle):
-    check(ga, oracle, cloud(21, (8, 2048, 3)), cloud(22, (8, 2048, 3)), cfgs=[1, 4, 21, 3021, 29021, 23, 3023, 29023])
-    check(ga, oracle, cloud(23, (9, 1000, 3)), cloud(24, (9, 777, 3)), cfgs=[21, 2021, 5021, 13021, 23, 2023, 5023, 13023])
+    check(ga, oracle, cloud(21, (8, 2048, 3)), cloud(22, (8, 2048, 3)), cfgs=[1, 4, 21, 3021, 29021, 23, 3023, 29023, 24, 3024, 29024])
+    check(ga, oracle, cloud(23, (9, 1000, 3)), cloud(24, (9, 777, 3)), cfgs=[21, 2021, 5021, 13021, 23, 2023, 5023, 13023, 24, 2024, 5024, 13024])
 
 
 def test_adversarial_duplicates_and_grids(ga, oracle):
@@ -111,7 +112,7 @@ def test_scales_and_offsets(ga, oracle):
     a, b = cloud(31, (1, 1500, 3)), cloud(32, (1, 1800, 3))
     for scale, off in [(1e3, 0.0), (1.0, 100.0), (1e-6, 0.0), (1e-18, 0.0), (1e15, 0.0), (1e-30, 0.0)]:
         check(ga, oracle, (a * np.float32(scale) + np.float32(off)).astype(np.float32),
-              (b * np.float32(scale) + np.float32(off)).astype(np.float32), cfgs=[1, 4, 21, 23])
+              (b * np.float32(scale) + np.float32(off)).astype(np.float32), cfgs=[1, 4, 21, 23, 24])
 
 
 def test_non_finite_inputs(ga, oracle):
@@ -121,8 +122,8 @@ def test_non_finite_inputs(ga, oracle):
     b[1, 17, 2] = np.inf
     a[1, 3, 0] = -np.inf
     b[1, 100] = 3e38             # overflowing distances
-    check(ga, oracle, a, b, cfgs=[1, 4, 21, 23])
-    check(ga, oracle, a, b, mode=1, cfgs=[1, 21, 23])
+    check(ga, oracle, a, b, cfgs=[1, 4, 21, 23, 24])
+    check(ga, oracle, a, b, mode=1, cfgs=[1, 21, 23, 24])
 
 
 def test_full_size_equals_plain_kernel(ga):

@@ -19,7 +19,13 @@ for (B, N, M) in shapes:
     d2 = torch.empty(B, M, device=dev); i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
     ref = None
     only = os.environ.get("TUNE_ONLY")
-    for name, keys in (("default", {}), ("hmma", {0: 20}), ("tc", {0: 22}), ("tc_dev", {0: 22, 20: 16}), ("tc_norefine", {0: 22, 20: 1}), ("tc_nohelper", {0: 22, 20: 9}), ("tc_neither", {0: 22, 20: 3}), ("tc_nohelper_nodrain", {0: 22, 20: 11})):
+    ROT = int(os.environ.get("ROTATE", "0"))  # >0: ROT input/output sets walked round-robin (total > L2) instead of the flush
+    if ROT:
+        xs1 = [x1.clone() for _ in range(ROT)]; xs2 = [x2.clone() for _ in range(ROT)]
+        ds1 = [torch.empty_like(d1) for _ in range(ROT)]; is1 = [torch.empty_like(i1) for _ in range(ROT)]
+        ds2 = [torch.empty_like(d2) for _ in range(ROT)]; is2 = [torch.empty_like(i2) for _ in range(ROT)]
+        rot = [0]
+    for name, keys in (("default", {}), ("hmma", {0: 20}), ("tc", {0: 22}), ("ws", {0: 24}), ("ws12", {0: 24, 22: 12}), ("ws_s2", {0: 24, 23: 2000}), ("ws_s4", {0: 24, 23: 4000}), ("ws_s6", {0: 24, 23: 6000}), ("ws_s8", {0: 24, 23: 8000}), ("tc_dev", {0: 22, 20: 16}), ("tc_norefine", {0: 22, 20: 1}), ("tc_nohelper", {0: 22, 20: 9}), ("tc_neither", {0: 22, 20: 3}), ("tc_nohelper_nodrain", {0: 22, 20: 11})):
         if only and name not in only.split(','):
             continue
         if (keys.get(20, 0) & 8) and B > 100:
@@ -27,6 +33,11 @@ for (B, N, M) in shapes:
         for k, v in keys.items():
             lib.ga_set_tuning(k, v)
         def call():
+            if ROT:
+                r = rot[0] = (rot[0] + 1) % ROT
+                _lib.check(lib.ga_nn_distance_fwd(B, N, M, p(xs1[r].data_ptr()), p(xs2[r].data_ptr()), p(ds1[r].data_ptr()), p(is1[r].data_ptr()),
+                                                  p(ds2[r].data_ptr()), p(is2[r].data_ptr()), 0, p(st)))
+                return
             _lib.check(lib.ga_nn_distance_fwd(B, N, M, p(x1.data_ptr()), p(x2.data_ptr()), p(d1.data_ptr()), p(i1.data_ptr()),
                                               p(d2.data_ptr()), p(i2.data_ptr()), 0, p(st)))
         try:
@@ -34,12 +45,13 @@ for (B, N, M) in shapes:
                 call()
             torch.cuda.synchronize()
             ts = []
-            for _ in range(20):
-                flush.zero_()
+            for _ in range(20 if not ROT else 3 * ROT):
+                if not ROT:
+                    flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); call(); e1.record(); torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1) * 1e3)
-            out = (d1.clone(), i1.clone(), d2.clone(), i2.clone())
+            out = (d1.clone(), i1.clone(), d2.clone(), i2.clone()) if not ROT else (ds1[rot[0]].clone(), is1[rot[0]].clone(), ds2[rot[0]].clone(), is2[rot[0]].clone())
             if ref is None:
                 ref = out
             same = all(torch.equal(a, b) for a, b in zip(out, ref))
