@@ -386,7 +386,7 @@ def run_ours(args):
         # the filter scan of nn_fwd_mma_kernel runs on the legacy warp MMA: its issue rate is what bounds the
         # kernel, so report it beside the FP32-peak fraction the metric asks for
         tensor_pipe = None
-        if fwd_kernel == "nn_fwd_mma_kernel":
+        if fwd_kernel.startswith("nn_fwd_mma_kernel"):
             hmma = 4.0 * B * (-(-N // 64) * (-(-M // 128) * 16) + -(-M // 64) * (-(-N // 128) * 16))
             sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
             sms = torch.cuda.get_device_properties(dev).multi_processor_count

@@ -35,6 +35,8 @@ extern int g_umma_auto;          // nn_distance_fwd.cu
 extern int g_ws_scan;            // nn_distance_fwd_mma_ws.cu
 extern int g_ws_idle_ns;         // nn_distance_fwd_mma_ws.cu
 extern int g_ws_dev;             // nn_distance_fwd_mma_ws.cu
+extern int g_frame;              // nn_distance_fwd_mma.cu
+extern std::atomic<int> g_frame_clear;
 static thread_local char t_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static thread_local const char* t_last_kernel = "";
@@ -93,6 +95,45 @@ unsigned long long* ticket_buffer(cudaStream_t st) {
     return expect;
   }
   return fresh;
+}
+
+// One pinned, device-mapped word per device: kernels that meet a cloud away from the origin set it, the launcher of
+// the tensor-core forward reads it (no synchronisation: a stale value costs time, never bits) to choose between its
+// plain and its centred-frame kernel.  Allocated at the first launch outside a stream capture.
+int* frame_hint(cudaStream_t st, volatile int** host_view) {
+  struct Hint { int* dev; volatile int* host; };
+  static std::atomic<Hint*> g_hint[32];
+  int dev = 0;
+  *host_view = nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  Hint* h = g_hint[dev].load(std::memory_order_acquire);
+  if (h == nullptr) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    int* hp = nullptr;
+    int* dp = nullptr;
+    if (cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (hp != nullptr) cudaFreeHost(hp);
+      return nullptr;
+    }
+    *hp = 0;
+    Hint* fresh = new Hint{dp, hp};
+    Hint* expect = nullptr;
+    if (!g_hint[dev].compare_exchange_strong(expect, fresh, std::memory_order_acq_rel)) {
+      cudaFreeHost(hp);  // another thread was faster
+      delete fresh;
+      h = expect;
+    } else {
+      h = fresh;
+    }
+  }
+  *host_view = h->host;
+  return h->dev;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -242,6 +283,11 @@ int ga_set_tuning(int key, int value) {
   }
   if (key == 24) {
     ga::g_ws_dev = value;
+    return GA_OK;
+  }
+  if (key == 25) {
+    ga::g_frame = value;
+    ga::g_frame_clear.store(1, std::memory_order_relaxed);
     return GA_OK;
   }
   if (key == 11) {

@@ -22,6 +22,7 @@ void note_kernel(const char* name);
 constexpr int kTicketSlots = 4096;  // + 8 words of debug counters behind the slots (ga_debug_ticket_stats)
 unsigned long long* ticket_buffer(cudaStream_t st);  // nullptr if it cannot be provided right now
 unsigned long long next_call_id();
+int* frame_hint(cudaStream_t st, volatile int** host_view);  // device view of the per-device hint word, or nullptr
 struct LastForward {  // the calling thread's most recent ticketed forward launch
   cudaStream_t stream;
   const int* idx1;
@@ -66,6 +67,12 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float d;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
 

@@ -326,7 +326,7 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   a.xyz1 = xyz1; a.xyz2 = xyz2;
   a.dist1 = dist1; a.idx1 = idx1; a.dist2 = dist2; a.idx2 = idx2;
   a.mdist1 = mdist1; a.midx1 = midx1; a.mdist2 = mdist2; a.midx2 = midx2;
-  a.ticket = nullptr; a.call_id = 0; a.ticket_debug = 0;
+  a.ticket = nullptr; a.call_id = 0; a.ticket_debug = 0; a.frame_hint = nullptr;
   last_forward().call_id = 0;  // only a ticketed launch below re-arms the gradient kernel's early start
   // Default: 4 queries per thread (FMA-pipe bound scan).  Small problems (few hundred query
   // tiles, e.g. the B=1 calls of autoencoder.py:150-168) take 2 queries per thread instead:

@@ -24,15 +24,20 @@ struct MmaCfg {
   static constexpr int kQT = WARPS * kMmaQW;  // queries per CTA
   static constexpr int kCH = CH;              // targets staged per chunk
   static_assert(CH % kMmaBlk == 0 && CH / kMmaBlk <= 16, "whole MMA blocks, block number must fit 4 key bits");
-  // pair-SoA (+pipeline pad) | red[32] | B fragments | per-query tile lists (count, 2 tiles)
+  // pair-SoA (+pipeline pad) | red[96] (stage_targets_min, frame_from_box) | B fragments | per-query tile lists (count, 2 tiles)
+  // The B fragments must start on a 128-byte line: a warp's LDS.64 covers 256 contiguous bytes, two wavefronts when
+  // aligned and three when not (measured: 56 -> 59 us at B=50 with the fragments 64 bytes off).
   static constexpr size_t kOffRed = (size_t)CH * 16 + (size_t)kPipeU * 32;
-  static constexpr size_t kOffB = kOffRed + 32 * 4;
+  static constexpr size_t kOffB = kOffRed + 96 * 4;
+  static_assert(kOffB % 128 == 0, "B fragments on a 128-byte line");
   static constexpr size_t kOffCnt = kOffB + (size_t)CH * 32;
   static constexpr size_t kOffTile = kOffCnt + (size_t)kQT * 4;
   static constexpr size_t kSmem = kOffTile + (size_t)kQT * 4;
 };
 
-template <class Cfg, int MODE, int MINB>
+// FRAME = false: the plain kernel; it only reports clouds that keep away from the origin (a.frame_hint).
+// FRAME = true: the filter of such a cloud runs in a frame centred on it (Frame, nn_tiles.cuh).  Same bits either way.
+template <class Cfg, int MODE, int MINB, bool FRAME>
 __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const FwdArgs a) {
   constexpr int THREADS = Cfg::kThreads, QT = Cfg::kQT, CH = Cfg::kCH, T = kMmaT;
   // Completion tickets: clear this batch element's slot BEFORE the dependents may start (a replayed CUDA
@@ -76,20 +81,79 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
 
   const int qbase = qtile * QT + warp * kMmaQW;  // first query of this warp
   MmaRows R;
-  mma_load_rows(R, qpts, nq, qbase, lane);
   QueryState<2> s;
-  mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane);
   float mrun[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
   float bm_run = 0.0f;
 
-  for (int c0 = 0; c0 < nt; c0 += CH) {
-    const int cn = min(CH, nt - c0);
-    bm_run = fmaxf(bm_run, stage_targets<THREADS, T>(tgt, red, tpts, c0, nt, (cn + T - 1) / T, tid));
-    stage_bfrag<THREADS>(bfrag, tgt, (cn + kMmaBlk - 1) / kMmaBlk, cn, tid);
-    __syncthreads();
-    mma_chunk<MODE>(R, s, mrun, tgt, bfrag, c0, nt, cn, bm_run, lcnt + warp * kMmaQW, ltile + warp * kMmaQW * 2, lane);
+  if constexpr (!FRAME) {
+    // the query side is built before the staging: its loads hide behind it
+    mma_load_rows(R, qpts, nq, qbase, lane);
+    mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane);
+    for (int c0 = 0; c0 < nt; c0 += CH) {
+      const int cn = min(CH, nt - c0);
+      float mn;
+      bm_run = fmaxf(bm_run, stage_targets_min<THREADS, T>(tgt, red, tpts, c0, nt, (cn + T - 1) / T, tid,
+                                                            c0 == 0 && a.frame_hint != nullptr, mn));
+      if (frame_candidate(mn, bm_run)) {  // uniform, rare; mn = 0 behind the first chunk
+        Frame fr;
+        if (frame_from_box<THREADS, T>(tgt, red, c0, nt, (cn + T - 1) / T, tid, fr) && tid == 0)
+          *reinterpret_cast<volatile int*>(a.frame_hint) = 1;
+      }
+      stage_bfrag<THREADS>(bfrag, tgt, (cn + kMmaBlk - 1) / kMmaBlk, cn, tid);
+      __syncthreads();
+      mma_chunk<MODE>(R, s, mrun, tgt, bfrag, c0, nt, cn, bm_run, lcnt + warp * kMmaQW, ltile + warp * kMmaQW * 2, lane);
+    }
+  } else {
+    // The frame is chosen behind the staging of the first chunk, and the query side is built for it after that.
+    // Between its uses the frame lives in shared memory: every value kept live across the scan costs the scan loop
+    // an accumulator quad.
+    volatile float* frs = red + 72;
+    {
+      const int ntile = (min(CH, nt) + T - 1) / T;
+      float mn;
+      bm_run = stage_targets_min<THREADS, T>(tgt, red, tpts, 0, nt, ntile, tid, true, mn);
+      Frame fr;
+      fr.cx = fr.cy = fr.cz = 0.0f;
+      fr.shifted = false;
+      if (frame_candidate(mn, bm_run) && frame_from_box<THREADS, T>(tgt, red, 0, nt, ntile, tid, fr))
+        bm_run = shift_staged<THREADS, T>(tgt, red, 0, nt, ntile, tid, fr);
+      const int t = lane & 3;
+      mma_load_rows(R, qpts, nq, qbase, lane, t == 0 ? fr.cx : (t == 1 ? fr.cy : fr.cz));
+      mma_init_queries<MODE>(s, qpts, nq, qbase, tpts, lane, fr.cx, fr.cy, fr.cz);
+      if (tid == 0) {
+        frs[0] = fr.cx;
+        frs[1] = fr.cy;
+        frs[2] = fr.cz;
+        frs[3] = fr.shifted ? 1.0f : 0.0f;
+      }
+    }
+    for (int c0 = 0; c0 < nt; c0 += CH) {
+      const int cn = min(CH, nt - c0), ntile = (cn + T - 1) / T;
+      if (c0 > 0) {
+        if (frs[3] != 0.0f) {
+          Frame fr;
+          fr.cx = frs[0];
+          fr.cy = frs[1];
+          fr.cz = frs[2];
+          fr.shifted = true;
+          bm_run = fmaxf(bm_run, stage_targets_shifted<THREADS, T>(tgt, red, tpts, c0, nt, ntile, tid, fr));
+        } else {
+          bm_run = fmaxf(bm_run, stage_targets<THREADS, T>(tgt, red, tpts, c0, nt, ntile, tid));
+        }
+      }
+      stage_bfrag<THREADS>(bfrag, tgt, (cn + kMmaBlk - 1) / kMmaBlk, cn, tid);
+      __syncthreads();
+      // two copies of the chunk body: in the unshifted one the "original coordinates" pointer is the constant
+      // nullptr and the compiler drops every trace of the shifted path from scan and refine
+      if (frs[3] != 0.0f)
+        mma_chunk<MODE>(R, s, mrun, tgt, bfrag, c0, nt, cn, bm_run, lcnt + warp * kMmaQW, ltile + warp * kMmaQW * 2,
+                        lane, tpts);
+      else
+        mma_chunk<MODE>(R, s, mrun, tgt, bfrag, c0, nt, cn, bm_run, lcnt + warp * kMmaQW, ltile + warp * kMmaQW * 2,
+                        lane, nullptr);
+    }
   }
   mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
             rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
@@ -504,6 +568,13 @@ __global__ void __launch_bounds__(Cfg::kThreads) mma_filter_dump_kernel(int n, i
   }
 }
 
+// tuning hook (key 25): 0 = plain kernel, never a frame; 1 = frame kernel always; 2 (default) = plain kernel until one
+// of its launches on this device has reported a cloud away from the origin (frame_hint, core.cu), frame kernel from
+// then on (setting the key again clears the report).  Both kernels return the same bits: the choice is about time
+// only (unit cubes at offset 10: 569 us plain, 61 us frame; centred: 56 vs 59).  A captured graph keeps the kernel
+// chosen at capture time.
+int g_frame = 2;
+std::atomic<int> g_frame_clear{0};  // set by ga_set_tuning(25, .): the next launch clears the device's report
 int g_tickets = 1;  // tuning hook (key 18): 0 = never, 1 = for ga_nn_distance_fwd_bwd only, 2 = always + debug stamps, 3 = always
 thread_local int t_want_tickets = 0;  // set by ga_nn_distance_fwd_bwd around its forward launch
 int g_mma_cfg = 0;  // tuning hook (key 7): 0 auto (= 5); 1-5 = (warps, chunk, CTAs/SM) combinations below
@@ -518,15 +589,29 @@ static int launch_fwd_mma_cfg(FwdArgs a, int mode, cudaStream_t st) {
     set_error("ga_nn_distance_fwd: problem too large for one launch (%lld CTAs)", jobs);
     return GA_ERR_UNSUPPORTED;
   }
-  auto k = mode == GA_MODE_CPU_EXACT ? nn_fwd_mma_kernel<Cfg, GA_MODE_CPU_EXACT, MINB>
-                                     : nn_fwd_mma_kernel<Cfg, GA_MODE_GPU_REF, MINB>;
+  a.frame_hint = nullptr;
+  bool frame = g_frame == 1;
+  if (g_frame == 2) {
+    volatile int* seen = nullptr;
+    a.frame_hint = frame_hint(st, &seen);
+    if (seen != nullptr) {
+      if (g_frame_clear.exchange(0, std::memory_order_relaxed)) *seen = 0;
+      frame = *seen != 0;
+    }
+  }
+  auto k = mode == GA_MODE_CPU_EXACT
+               ? (frame ? nn_fwd_mma_kernel<Cfg, GA_MODE_CPU_EXACT, MINB, true>
+                        : nn_fwd_mma_kernel<Cfg, GA_MODE_CPU_EXACT, MINB, false>)
+               : (frame ? nn_fwd_mma_kernel<Cfg, GA_MODE_GPU_REF, MINB, true>
+                        : nn_fwd_mma_kernel<Cfg, GA_MODE_GPU_REF, MINB, false>);
   {
-    static std::atomic<unsigned> done_mask[2];
+    static std::atomic<unsigned> done_mask[4];
+    const int slot = mode * 2 + (frame ? 1 : 0);
     int dev = 0;
     GA_CUDA_TRY(cudaGetDevice(&dev));
-    if (!(done_mask[mode].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
+    if (!(done_mask[slot].load(std::memory_order_relaxed) & (1u << (dev & 31)))) {
       GA_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-      done_mask[mode].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
+      done_mask[slot].fetch_or(1u << (dev & 31), std::memory_order_relaxed);
     }
   }
   // arm the completion tickets (see the end of the kernel); off for batches beyond the slot count
@@ -541,7 +626,7 @@ static int launch_fwd_mma_cfg(FwdArgs a, int mode, cudaStream_t st) {
   }
   a.ticket_debug = g_tickets == 2;
   k<<<(unsigned)jobs, Cfg::kThreads, Cfg::kSmem, st>>>(a);
-  GA_LAUNCH_CHECK("nn_fwd_mma_kernel");
+  GA_LAUNCH_CHECK(frame ? "nn_fwd_mma_kernel<frame>" : "nn_fwd_mma_kernel");
   if (a.call_id != 0) {
     LastForward& lf = last_forward();
     lf.stream = st;

@@ -142,17 +142,26 @@ struct MmaRows {
 // Quad lane t < 3 loads and splits coordinate t of each of its rows (A slots C1, C1, C2, 1); lane 3
 // needs the three residuals (X2, Y2, Z2, 0), which it gets from lanes 0..2 by shuffle.  The max
 // |coordinate| of a row is a quad reduction (+inf when a coordinate is NaN, as query_abs).
-__device__ __forceinline__ void mma_load_rows(MmaRows& R, const float* __restrict__ qpts, int nq, int qbase,
-                                              int lane) {
+// The raw coordinate (t < 3 ? t : 2) of each of the lane's 8 rows: issued early, used by mma_build_rows.
+__device__ __forceinline__ void mma_fetch_rows(float (&qraw)[8], const float* __restrict__ qpts, int nq, int qbase,
+                                               int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int cc = t < 3 ? t : 2;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int qi = qbase + 16 * (r >> 1) + g + 8 * (r & 1);
+    const int qs = qi < nq ? qi : 0;
+    qraw[r] = __ldg(qpts + (size_t)qs * 3 + cc);
+  }
+}
+// shift: this lane's component (coordinate t < 3 ? t : 2) of the frame centre (Frame, nn_tiles.cuh); 0 = no shift.
+__device__ __forceinline__ void mma_build_rows(MmaRows& R, const float (&qraw)[8], int lane, float shift) {
+  const int t = lane & 3;
   const unsigned qbaseLane = lane & ~3;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const int i = r >> 1, h = r & 1;
-    const int qi = qbase + 16 * i + g + 8 * h;
-    const int qs = qi < nq ? qi : 0;
-    const float q = __ldg(qpts + (size_t)qs * 3 + cc);
+    const float q = qraw[r] - shift;
     const float C = -2.0f * q;
     const float Cr = C - bf16r(C);
     const float Xr = __shfl_sync(0xffffffffu, Cr, qbaseLane), Yr = __shfl_sync(0xffffffffu, Cr, qbaseLane + 1),
@@ -166,6 +175,12 @@ __device__ __forceinline__ void mma_load_rows(MmaRows& R, const float* __restric
     a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 2));
     R.qabs[r] = a;
   }
+}
+__device__ __forceinline__ void mma_load_rows(MmaRows& R, const float* __restrict__ qpts, int nq, int qbase,
+                                              int lane, float shift = 0.0f) {
+  float qraw[8];
+  mma_fetch_rows(qraw, qpts, nq, qbase, lane);
+  mma_build_rows(R, qraw, lane, shift);
 }
 
 // Sentinel for "no value": finite, so that a key never turns into a NaN bit pattern.
@@ -299,10 +314,11 @@ __device__ __forceinline__ void tile_candidate_mask2(const float4* __restrict__ 
 //  2. second tiles are rare (a few per warp): the whole warp evaluates such a tile exactly, one
 //     target per lane, and merges by (value, index);
 //  3. cnt > 2 / many candidates / non-finite window: warp_exact_scan (nn_search.cuh).
+// torig != nullptr: staged copy and s.ax2.. are in a shifted frame; exact evaluations read the original target.
 template <int MODE, int Q = 2>
 __device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __restrict__ tgt, int c0, int nt,
                                              int ntile, const int (&cnt)[Q], const int (&ta)[Q], const int (&tb)[Q],
-                                             const float (&thr)[Q]) {
+                                             const float (&thr)[Q], const float* __restrict__ torig = nullptr) {
   constexpr int T = kMmaT;
   const int lane = threadIdx.x & 31;
   bool hard[Q], second[Q];
@@ -333,9 +349,9 @@ __device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __r
     mask &= rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
     const int n = __popc(mask);
     if (n >= 1 && n <= 2)
-      eval_candidate<MODE>(tgt, c0, g0 + __ffs(mask) - 1, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+      eval_candidate<MODE>(tgt, c0, g0 + __ffs(mask) - 1, s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j], torig);
     if (n == 2)
-      eval_candidate<MODE>(tgt, c0, g0 + 31 - __clz(mask), s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j]);
+      eval_candidate<MODE>(tgt, c0, g0 + 31 - __clz(mask), s.qx[j], s.qy[j], s.qz[j], s.best[j], s.besti[j], torig);
     if (n > 2) {
       hard[j] = true;
       second[j] = false;
@@ -355,7 +371,13 @@ __device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __r
       float b = __int_as_float(0x7f800000);
       int bi = 0x7fffffff;
       if (c0 + gl < nt) {
-        const float d = sqdist<MODE>(pu[0], pu[2], pu[4], bqx, bqy, bqz);
+        float tx = pu[0], ty = pu[2], tz = pu[4];
+        if (torig != nullptr) {
+          tx = __ldg(torig + (size_t)(c0 + gl) * 3);
+          ty = __ldg(torig + (size_t)(c0 + gl) * 3 + 1);
+          tz = __ldg(torig + (size_t)(c0 + gl) * 3 + 2);
+        }
+        const float d = sqdist<MODE>(tx, ty, tz, bqx, bqy, bqz);
         if (d < b) {  // NaN is never selected
           b = d;
           bi = c0 + gl;
@@ -389,7 +411,7 @@ __device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __r
       const float bthr = __shfl_sync(0xffffffffu, thr[j], src);
       float b;
       int bi;
-      warp_exact_scan<MODE>(tgt, c0, nt, ntile * (T / 2), bqx, bqy, bqz, bax, bay, baz, bthr, b, bi, lane);
+      warp_exact_scan<MODE>(tgt, c0, nt, ntile * (T / 2), bqx, bqy, bqz, bax, bay, baz, bthr, b, bi, lane, torig);
       if (lane == src && (b < s.best[j] || (b == s.best[j] && bi < s.besti[j]))) {
         s.best[j] = b;
         s.besti[j] = bi;
@@ -402,9 +424,11 @@ __device__ __forceinline__ void refine_tiles(QueryState<Q>& s, const float4* __r
 
 // The two queries a lane refines and writes: m-tile t = lane&3, rows g = lane>>2 and g+8 of the
 // warp's 64 queries, i.e. local queries 16 t + g + 8 j.
+// (cx, cy, cz): centre of the filter's frame; qx.. and d0 stay in original coordinates, the filter side is shifted.
 template <int MODE>
 __device__ __forceinline__ void mma_init_queries(QueryState<2>& s, const float* __restrict__ qpts, int nq, int qbase,
-                                                 const float* __restrict__ tpts, int lane) {
+                                                 const float* __restrict__ tpts, int lane, float cx = 0.0f,
+                                                 float cy = 0.0f, float cz = 0.0f) {
   const float kInf = __int_as_float(0x7f800000);
   const int g = lane >> 2, t = lane & 3;
   const float t0x = __ldg(tpts), t0y = __ldg(tpts + 1), t0z = __ldg(tpts + 2);
@@ -416,17 +440,16 @@ __device__ __forceinline__ void mma_init_queries(QueryState<2>& s, const float* 
     s.qx[j] = __ldg(qpts + (size_t)qs * 3);
     s.qy[j] = __ldg(qpts + (size_t)qs * 3 + 1);
     s.qz[j] = __ldg(qpts + (size_t)qs * 3 + 2);
-    s.qabs[j] = query_abs(s.qx[j], s.qy[j], s.qz[j]);
-    s.ax2[j] = -2.0f * s.qx[j];
-    s.ay2[j] = -2.0f * s.qy[j];
-    s.az2[j] = -2.0f * s.qz[j];
+    s.qabs[j] = query_abs(s.qx[j] - cx, s.qy[j] - cy, s.qz[j] - cz);
+    s.ax2[j] = -2.0f * (s.qx[j] - cx);
+    s.ay2[j] = -2.0f * (s.qy[j] - cy);
+    s.az2[j] = -2.0f * (s.qz[j] - cz);
     s.d0[j] = sqdist<MODE>(t0x, t0y, t0z, s.qx[j], s.qy[j], s.qz[j]);
     s.best[j] = kInf;
     s.besti[j] = 0;
     s.m1g[j] = kInf;
   }
 }
-
 // One staged chunk (targets [c0, c0 + cn) of a cloud with nt points) for one warp: tensor-core
 // scan, per-query lists of the qualifying tiles, exact refine.  mrun: running row minima of h over
 // the chunks seen so far (same value in the 4 lanes of a quad); wcnt / wtile: this warp's lists.
@@ -434,7 +457,8 @@ template <int MODE>
 __device__ __forceinline__ void mma_chunk(const MmaRows& R, QueryState<2>& s, float (&mrun)[8],
                                           const float4* __restrict__ tgt, const uint4* __restrict__ bfrag, int c0, int nt,
                                           int cn, float bm_run, int* __restrict__ wcnt,
-                                          unsigned short* __restrict__ wtile, int lane) {
+                                          unsigned short* __restrict__ wtile, int lane,
+                                          const float* __restrict__ torig = nullptr) {
   constexpr int T = kMmaT;
   const int g = lane >> 2, t = lane & 3;
   const int ntile = (cn + T - 1) / T;
@@ -479,9 +503,10 @@ __device__ __forceinline__ void mma_chunk(const MmaRows& R, QueryState<2>& s, fl
     // a tile id beyond the staged tiles can only come from padding under a non-finite window
     if ((cnt[j] >= 1 && ta[j] >= ntile) || (cnt[j] >= 2 && tb[j] >= ntile)) cnt[j] = 3;
   }
-  refine_tiles<MODE>(s, tgt, c0, nt, ntile, cnt, ta, tb, mythr);
+  refine_tiles<MODE>(s, tgt, c0, nt, ntile, cnt, ta, tb, mythr, torig);
   __syncwarp();  // lists are reused by the next chunk / job
 }
+
 
 __device__ __forceinline__ void mma_write(const QueryState<2>& s, int qbase, int lane, float* __restrict__ odist,
                                           int* __restrict__ oidx, float* __restrict__ mdist, int* __restrict__ midx,

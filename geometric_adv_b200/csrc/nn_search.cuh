@@ -27,6 +27,7 @@ struct FwdArgs {
   unsigned long long* ticket;
   unsigned long long call_id;
   int ticket_debug;
+  int* frame_hint;  // device view of the launcher's off-origin hint word (nn_distance_fwd_mma.cu), or nullptr
 };
 
 template <int THREADS, int Q, int T, int CH>
@@ -69,12 +70,21 @@ __device__ __forceinline__ void scan_tile_candidates(const float4* __restrict__ 
 }
 
 // Reference arithmetic for one staged target (index g in the chunk starting at c0).
+// torig != nullptr: the staged copy is in a shifted frame (Frame, nn_tiles.cuh); the target's original coordinates
+// are fetched from its cloud in global memory (torig = first point of the cloud).
 template <int MODE>
 __device__ __forceinline__ void eval_candidate(const float4* __restrict__ tgt, int c0, int g, float qx, float qy,
-                                               float qz, float& best, int& besti) {
+                                               float qz, float& best, int& besti,
+                                               const float* __restrict__ torig = nullptr) {
   const int p = (g - c0) >> 1, h = (g - c0) & 1;
   const float* pu = reinterpret_cast<const float*>(tgt + 2 * p);
-  const float d = sqdist<MODE>(pu[h], pu[2 + h], pu[4 + h], qx, qy, qz);
+  float tx = pu[h], ty = pu[2 + h], tz = pu[4 + h];
+  if (torig != nullptr) {
+    tx = __ldg(torig + (size_t)g * 3);
+    ty = __ldg(torig + (size_t)g * 3 + 1);
+    tz = __ldg(torig + (size_t)g * 3 + 2);
+  }
+  const float d = sqdist<MODE>(tx, ty, tz, qx, qy, qz);
   if (d < best || (d == best && g < besti)) {
     best = d;
     besti = g;
@@ -89,7 +99,8 @@ __device__ __forceinline__ void eval_candidate(const float4* __restrict__ tgt, i
 template <int MODE>
 __device__ __forceinline__ void warp_exact_scan(const float4* __restrict__ tgt, int c0, int nt, int npair,
                                                 float qx, float qy, float qz, float ax2, float ay2, float az2,
-                                                float thr, float& b, int& bi, int lane) {
+                                                float thr, float& b, int& bi, int lane,
+                                                const float* __restrict__ torig = nullptr) {
   b = __int_as_float(0x7f800000);
   bi = 0x7fffffff;
   for (int p = lane; p < npair; p += 32) {
@@ -98,14 +109,26 @@ __device__ __forceinline__ void warp_exact_scan(const float4* __restrict__ tgt, 
     const float2 f = filter_pair(u, v, ax2, ay2, az2);
     const int g = c0 + 2 * p;
     if (!(f.x > thr) && g < nt) {
-      const float d = sqdist<MODE>(u.x, u.z, v.x, qx, qy, qz);
+      float tx = u.x, ty = u.z, tz = v.x;
+      if (torig != nullptr) {
+        tx = __ldg(torig + (size_t)g * 3);
+        ty = __ldg(torig + (size_t)g * 3 + 1);
+        tz = __ldg(torig + (size_t)g * 3 + 2);
+      }
+      const float d = sqdist<MODE>(tx, ty, tz, qx, qy, qz);
       if (d < b || (d == b && g < bi)) {
         b = d;
         bi = g;
       }
     }
     if (!(f.y > thr) && g + 1 < nt) {
-      const float d = sqdist<MODE>(u.y, u.w, v.y, qx, qy, qz);
+      float tx = u.y, ty = u.w, tz = v.y;
+      if (torig != nullptr) {
+        tx = __ldg(torig + (size_t)(g + 1) * 3);
+        ty = __ldg(torig + (size_t)(g + 1) * 3 + 1);
+        tz = __ldg(torig + (size_t)(g + 1) * 3 + 2);
+      }
+      const float d = sqdist<MODE>(tx, ty, tz, qx, qy, qz);
       if (d < b || (d == b && g + 1 < bi)) {
         b = d;
         bi = g + 1;

@@ -219,7 +219,17 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  *      drain, bit 3 no helper, bits 8.. traced CTA (0 = product build)   21 automatic choice of the tcgen05 kernel
  *      between the HMMA kernel's wave steps (1)   22 variant 24: scan warps (0 = 8; 8 or 12 of 16)   23 variant 24: start
  *      offset of every scheduler's second scan warp, ns (0)   24 variant 24, development: bit 0 no refine, bit 1 no
- *      query loads in the scan warps (wrong results; timing only) */
+ *      query loads in the scan warps (wrong results; timing only)
+ *   25 frame of the HMMA grid kernel's filter (2): 0 = origin, always; 1 = centred on the target cloud where that cloud
+ *      keeps away from the origin (nn_fwd_mma_kernel<frame>); 2 = the plain kernel until one of its launches on the
+ *      device has met such a cloud (it reports through a word of mapped host memory, read without synchronisation at
+ *      the next launch), the frame kernel from then on; setting the key clears the report.
+ * Clouds far from the origin (relative to their size): the filters' windows scale with (max|q_c| + max|t_c|)^2 measured
+ * from the origin of the frame they are evaluated in, so a unit cube at offset 10 costs the plain tensor-core forward
+ * 569 us instead of 57 (B=50, 2048 points); the frame kernel takes 63.5 us at any offset, and 57 on centred clouds
+ * (profiles/r02_tune_offset.txt).  Results are the same bits in every frame.  The first launch that meets such clouds
+ * is a plain one; a captured graph keeps the kernel chosen at capture time (set key 25 = 1 before capturing if the
+ * clouds are known to sit away from the origin).  The fp32-filter kernels, kNN and all-pairs keep the origin frame. */
 int ga_set_tuning(int key, int value);
 /* Empty-kernel launch floor in microseconds (average over `reps` launches). */
 int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);

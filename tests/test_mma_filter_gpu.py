@@ -235,3 +235,72 @@ def test_filter_bound_hypothesis(ga):
         assert np.abs(h - g).max() <= 330.0 * U * s * s
 
     run()
+
+
+@pytest.mark.parametrize("off", [(0.5, 0.5, 0.5), (3.0, -2.0, 0.25), (-10.0, 10.0, 10.0), (1000.0, 0.0, -1000.0)])
+def test_off_origin_clouds_use_a_centred_frame_and_stay_bit_exact(ga, oracle, off):
+    """Clouds away from the origin: the frame kernel (nn_fwd_mma_kernel<..., FRAME = true>, forced with key 25 = 1)
+    evaluates its filter in a frame centred on the target cloud (Frame, nn_tiles.cuh); the results are the reference's
+    bits, whatever the frame."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    o = np.asarray(off, np.float32)
+    a = (cloud(51, (3, 2048, 3)) + o).astype(np.float32)
+    b = (cloud(52, (3, 2048, 3)) + o).astype(np.float32)
+    lib.ga_set_tuning(25, 1)
+    try:
+        check(ga, oracle, a, b, cfgs=[1, 2, 3, 4, 5])
+        assert lib.ga_last_kernel().decode() == "nn_fwd_mma_kernel<frame>"
+        check(ga, oracle, a, b, mode=1, cfgs=[5])
+        # the query cloud somewhere else than the target cloud; ragged sizes; a chunked cloud (frame kept over chunks)
+        check(ga, oracle, (a[:2, :700] - 2 * o).astype(np.float32), b[:2, :1999], cfgs=[1, 5])
+        big = (cloud(53, (1, 5000, 3)) * np.float32(2.0) + o).astype(np.float32)
+        check(ga, oracle, a[:1, :300], big, cfgs=[1, 4, 5])
+        # exact ties inside an offset cloud, and non-finite points (such a cloud keeps c = 0)
+        check(ga, oracle, a[:1], a[:1].copy(), cfgs=[5])
+        c, d = a[:2, :900].copy(), b[:2, :800].copy()
+        c[0, 5, 1] = np.nan
+        d[0, 0, 0] = np.nan
+        d[1, 17, 2] = np.inf
+        c[1, 3, 0] = -np.inf
+        check(ga, oracle, c, d, cfgs=[1, 5])
+        # a centred cloud and a shell around the origin (candidate by its points, centred by its box) keep c = 0
+        check(ga, oracle, cloud(54, (2, 600, 3)), cloud(55, (2, 700, 3)), cfgs=[5])
+        sh = cloud(56, (2, 1500, 3))
+        sh = (sh / np.abs(sh).max(axis=2, keepdims=True)).astype(np.float32)  # surface of a cube
+        check(ga, oracle, sh[:, :800], sh, cfgs=[1, 5])
+    finally:
+        lib.ga_set_tuning(25, 2)
+
+
+def test_default_dispatch_switches_to_the_frame_kernel_once_an_off_origin_cloud_was_seen(ga, oracle):
+    """Key 25 = 2 (default): the plain kernel reports a cloud away from the origin through a word of mapped host
+    memory; launches after that take the frame kernel.  Shells around the origin and centred clouds do not report."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+
+    def run(a, b):
+        lib.ga_set_tuning(0, 20)
+        try:
+            got = [x.cpu().numpy() for x in ga.nn_distance(t(a), t(b))]  # .cpu() synchronises: the report has landed
+        finally:
+            lib.ga_set_tuning(0, 0)
+        for g, w in zip(got, oracle.nn_distance(a, b, 0)):
+            assert bits_equal(g, w)
+        return lib.ga_last_kernel().decode()
+
+    lib.ga_set_tuning(25, 2)  # clears an earlier report
+    try:
+        cen = cloud(61, (2, 1024, 3))
+        sh = (cen / np.abs(cen).max(axis=2, keepdims=True)).astype(np.float32)
+        off = (cen + np.float32(7.0)).astype(np.float32)
+        assert run(cen, cen[::-1].copy()) == "nn_fwd_mma_kernel"
+        assert run(sh, cen) == "nn_fwd_mma_kernel"
+        assert run(cen, sh) == "nn_fwd_mma_kernel", "a shell around the origin must not report"
+        assert run(off, off[::-1].copy()) == "nn_fwd_mma_kernel", "the reporting launch itself is a plain one"
+        assert run(off, off[::-1].copy()) == "nn_fwd_mma_kernel<frame>"
+        assert run(cen, cen[::-1].copy()) == "nn_fwd_mma_kernel<frame>", "the report is sticky"
+        lib.ga_set_tuning(25, 2)
+        assert run(cen, cen[::-1].copy()) == "nn_fwd_mma_kernel", "setting the key clears it"
+    finally:
+        lib.ga_set_tuning(25, 2)

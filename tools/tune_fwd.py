@@ -25,7 +25,7 @@ for (B, N, M) in shapes:
         ds1 = [torch.empty_like(d1) for _ in range(ROT)]; is1 = [torch.empty_like(i1) for _ in range(ROT)]
         ds2 = [torch.empty_like(d2) for _ in range(ROT)]; is2 = [torch.empty_like(i2) for _ in range(ROT)]
         rot = [0]
-    for name, keys in (("default", {}), ("hmma", {0: 20}), ("tc", {0: 22}), ("ws", {0: 24}), ("ws12", {0: 24, 22: 12}), ("ws_s2", {0: 24, 23: 2000}), ("ws_s4", {0: 24, 23: 4000}), ("ws_s6", {0: 24, 23: 6000}), ("ws_s8", {0: 24, 23: 8000}), ("tc_dev", {0: 22, 20: 16}), ("tc_norefine", {0: 22, 20: 1}), ("tc_nohelper", {0: 22, 20: 9}), ("tc_neither", {0: 22, 20: 3}), ("tc_nohelper_nodrain", {0: 22, 20: 11})):
+    for name, keys in (("default", {}), ("hmma", {0: 20}), ("hmma_frame", {0: 20, 25: 1}), ("tc", {0: 22}), ("ws", {0: 24}), ("ws12", {0: 24, 22: 12}), ("ws_s2", {0: 24, 23: 2000}), ("ws_s4", {0: 24, 23: 4000}), ("ws_s6", {0: 24, 23: 6000}), ("ws_s8", {0: 24, 23: 8000}), ("tc_dev", {0: 22, 20: 16}), ("tc_norefine", {0: 22, 20: 1}), ("tc_nohelper", {0: 22, 20: 9}), ("tc_neither", {0: 22, 20: 3}), ("tc_nohelper_nodrain", {0: 22, 20: 11})):
         if only and name not in only.split(','):
             continue
         if (keys.get(20, 0) & 8) and B > 100:
@@ -60,6 +60,6 @@ for (B, N, M) in shapes:
         except Exception as e:  # noqa: BLE001
             print(B, N, M, name, "failed:", e, flush=True)
         for k in keys:
-            lib.ga_set_tuning(k, 0)
+            lib.ga_set_tuning(k, 2 if k == 25 else 0)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_fwd.json"), "w"), indent=1)
