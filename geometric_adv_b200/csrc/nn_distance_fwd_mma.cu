@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
                         lane, nullptr);
     }
   }
-  mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
+  mma_write(s, qbase, nq, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
             rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
   // Completion ticket of this batch element: (call id << 16 | CTAs done).  The gradient kernel, started
   // early as a programmatic dependent, builds its inverse index map as soon as all CTAs of an element
@@ -218,7 +218,7 @@ __device__ __noinline__ void persist_job(const FwdArgs& a, int batch, bool rev, 
 #pragma unroll
   for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
   mma_chunk<MODE>(R, s, mrun, tgt, bfrag, 0, nt, nt, bm, wcnt, wtile, lane);
-  mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
+  mma_write(s, qbase, nq, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
             rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
 }
 
@@ -404,7 +404,7 @@ __device__ __noinline__ void balanced_part(const FwdArgs& a, const volatile int*
     cnt[j] = c;
   }
   refine_tiles<MODE>(s, tgt, 0, nt, ntile, cnt, ta, tb, thr);
-  mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
+  mma_write(s, qbase, nq, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
             rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
 }
 

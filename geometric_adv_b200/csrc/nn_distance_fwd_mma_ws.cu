@@ -145,7 +145,7 @@ __device__ __noinline__ void ws_refine_job(const FwdArgs& a, int batch, bool rev
     if ((cnt[j] >= 1 && ta[j] >= ntile) || (cnt[j] >= 2 && tb[j] >= ntile)) cnt[j] = 3;
   }
   refine_tiles<MODE>(s, tgt, 0, nt, ntile, cnt, ta, tb, thr);
-  mma_write(s, qbase, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
+  mma_write(s, qbase, nq, lane, (rev ? a.dist2 : a.dist1) + (size_t)batch * nq, (rev ? a.idx2 : a.idx1) + (size_t)batch * nq,
             rev ? a.mdist2 : a.mdist1, rev ? a.midx2 : a.midx1, (size_t)batch * nq);
 }
 

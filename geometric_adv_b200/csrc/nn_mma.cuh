@@ -508,22 +508,33 @@ __device__ __forceinline__ void mma_chunk(const MmaRows& R, QueryState<2>& s, fl
 }
 
 
-__device__ __forceinline__ void mma_write(const QueryState<2>& s, int qbase, int lane, float* __restrict__ odist,
+// Results of a warp's 64 queries.  A lane holds local queries 16 t + g + 8 j; they are transposed by shuffle so that
+// lane L writes local queries L and 32 + L: four full 128-byte lines per warp and array instead of sixteen 32-byte
+// pieces (what matters when mdist / midx are pinned host buffers: the stores are posted writes over PCIe).
+// Every lane of the warp must call it.  nq: queries of the cloud (rows beyond it are not written).
+__device__ __forceinline__ void mma_write(const QueryState<2>& s, int qbase, int nq, int lane, float* __restrict__ odist,
                                           int* __restrict__ oidx, float* __restrict__ mdist, int* __restrict__ midx,
                                           size_t moff) {
-  const int g = lane >> 2, t = lane & 3;
+  float d[2];
+  int i[2];
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
-    if (!s.valid[j]) continue;
-    const int qi = qbase + 16 * t + g + 8 * j;
-    float d;
-    int i;
-    finish_query<2>(s, j, d, i);
-    odist[qi] = d;
-    oidx[qi] = i;
-    if (mdist != nullptr) {
-      mdist[moff + qi] = d;
-      midx[moff + qi] = i;
+  for (int j = 0; j < 2; j++) finish_query<2>(s, j, d[j], i[j]);
+  const int jj = (lane >> 3) & 1;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int src = (lane & 7) * 4 + (lane >> 4) + 2 * h;  // holder of local query 32 h + lane, in its slot jj
+    const float d0 = __shfl_sync(0xffffffffu, d[0], src), d1 = __shfl_sync(0xffffffffu, d[1], src);
+    const int i0 = __shfl_sync(0xffffffffu, i[0], src), i1 = __shfl_sync(0xffffffffu, i[1], src);
+    const int qi = qbase + 32 * h + lane;
+    if (qi < nq) {
+      const float dv = jj ? d1 : d0;
+      const int iv = jj ? i1 : i0;
+      odist[qi] = dv;
+      oidx[qi] = iv;
+      if (mdist != nullptr) {
+        mdist[moff + qi] = dv;
+        midx[moff + qi] = iv;
+      }
     }
   }
 }
