@@ -26,6 +26,7 @@ SIGNATURES = {
     "ga_last_error": (C.c_char_p, []),
     "ga_launch_count": (C.c_longlong, []),
     "ga_last_kernel": (C.c_char_p, []),
+    "ga_debug_host_streamed": (C.c_int, []),
     "ga_check_nn_distance": (_i, [_i, _ll, _i, _ll]),
     "ga_check_nn_distance_grad": (_i, [_i, _ll, _i, _ll, _i, _ll, _i, _ll, _i, _ll, _i, _ll]),
     "ga_check_selection_sort": (_i, [_i, _i, _ll]),

@@ -32,6 +32,14 @@ struct LastForward {  // the calling thread's most recent ticketed forward launc
   unsigned long long* ticket;
 };
 LastForward& last_forward();
+// Streamed ingest (FwdArgs::ready, nn_search.cuh): the host entry arms the calling thread's next forward launch.
+struct ReadyArm {
+  const int* flags;
+  int per;
+  int* abort_word;
+};
+extern thread_local ReadyArm t_ready_arm;                // nn_distance_fwd_mma.cu
+bool fwd_ready_supported(int b, int n, int m);          // nn_distance_fwd.cu: would that launch honour the flags?
 int sm_count();
 
 #define GA_CUDA_TRY(expr)                                   \

@@ -19,6 +19,12 @@ struct Arena {
   cudaStream_t k_lane[8] = {};
   cudaEvent_t ev[48] = {};
   unsigned long long generation = 0;  // bumped when `base` moves: cached graphs hold device addresses
+  // streamed ingest (issue_pipeline_streamed): per-group arrival flags on the device, the pinned word the flag
+  // copies read, and the mapped word a CTA raises when it gave up waiting
+  int* d_ready = nullptr;
+  int* h_one = nullptr;
+  int* h_abort = nullptr;
+  int* d_abort = nullptr;
   // deliberately no destructor: at process teardown the CUDA context may already be gone
 };
 static thread_local Arena t_arena;
@@ -41,6 +47,11 @@ static int arena_reserve(size_t bytes, char** base, cudaStream_t* st) {
       if (e) cudaEventDestroy(e);
       e = nullptr;
     }
+    if (A.d_ready) cudaFree(A.d_ready);
+    if (A.h_one) cudaFreeHost(A.h_one);
+    if (A.h_abort) cudaFreeHost(A.h_abort);
+    A.d_ready = nullptr;
+    A.h_one = A.h_abort = A.d_abort = nullptr;
     A.generation++;
     A.base = nullptr;
     A.cap = 0;
@@ -163,6 +174,7 @@ static bool device_can_touch(const void* p) {
 int g_host_graph = 0;         // tuning hook (key 10): 0 auto, 1 never replay, 2 capture on first sight
 int g_host_graph_chunks = 0;  // tuning hook (key 11): chunks of the captured pipeline (0 = auto)
 int g_host_graph_epoch = 0;   // bumped by ga_set_tuning(10 | 11 | 17): cached graphs of older epochs are dropped
+int g_host_stream = 0;        // tuning hook (key 26): streamed ingest of the replayed step: 0 off, n = arrival groups
 int g_host_graph_mirror = 0;  // tuning hook (key 17): 0 auto, 1 = always copy dist/idx, 2 = always let the forward
                               // kernel write them straight to the pinned host buffers inside the replayed graph
 
@@ -170,11 +182,14 @@ struct HostGraph {
   cudaGraphExec_t exec = nullptr;
   int dev = -1, b = 0, n = 0, m = 0, mode = 0, nchunk = 0, launches = 0, seen = 0;
   bool failed = false;
+  bool streamed = false;   // exec is the streamed pipeline
+  bool no_stream = false;  // a streamed replay gave up waiting once: this key stays on the chunked pipeline
   const void* ptr[10] = {};
   unsigned long long generation = 0, stamp = 0;
   int epoch = 0;
 };
 static thread_local HostGraph t_graphs[4];
+static thread_local int t_last_streamed = 0;  // ga_debug_host_streamed
 static thread_local unsigned long long t_graph_clock = 0;
 long long launch_count_now();  // core.cu
 
@@ -195,6 +210,83 @@ struct FwdBwdBufs {
   int *d_i1, *d_i2;
   bool mirror;  // dist/idx host buffers are device-accessible: the forward kernel mirrors its outputs there
 };
+
+constexpr int kMaxReadyGroups = 32;
+
+// Buffers of the streamed pipeline; called outside any capture.
+static int stream_buffers() {
+  Arena& A = t_arena;
+  if (!A.d_ready) GA_CUDA_TRY(cudaMalloc(&A.d_ready, sizeof(int) * kMaxReadyGroups));
+  if (!A.h_one) {
+    GA_CUDA_TRY(cudaHostAlloc(&A.h_one, sizeof(int), cudaHostAllocDefault));
+    *A.h_one = 1;
+  }
+  if (!A.h_abort) {
+    GA_CUDA_TRY(cudaHostAlloc(&A.h_abort, sizeof(int), cudaHostAllocMapped));
+    *A.h_abort = 0;
+    GA_CUDA_TRY(cudaHostGetDevicePointer(&A.d_abort, A.h_abort, 0));
+  }
+  return GA_OK;
+}
+
+// The step with streamed ingest (wait_ready, nn_search.cuh): ONE forward launch for the whole batch, started at
+// the same time as the first H2D copy.  The clouds arrive in `groups` groups of batch elements, each followed by a
+// 4-byte copy that raises the group's flag; the CTAs of a batch element wait for it.  The search of group g runs
+// under the copy of group g+1, and no launch is split (a split launch pays the kernel's wave steps per piece:
+// two halves of B=50 cost 2 x 41 us instead of 56).  The upstream gradients follow the clouds on the same lane;
+// the rest is issue_pipeline with one chunk.
+static int issue_pipeline_streamed(const FwdBwdBufs& f, int b, int n, int m, int mode, int groups) {
+  Arena& A = t_arena;
+  cudaStream_t sin = A.stream, sout = A.out_lane, sk = A.k_lane[0];
+  cudaEvent_t fork = A.ev[0], join = A.ev[1], ev_g = A.ev[10], ev_f = A.ev[18], ev_b = A.ev[26];
+  const int per = (b + groups - 1) / groups;
+  groups = (b + per - 1) / per;
+  GA_CUDA_TRY(cudaMemsetAsync(A.d_ready, 0, sizeof(int) * groups, sin));
+  GA_CUDA_TRY(cudaEventRecord(fork, sin));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sout, fork, 0));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sk, fork, 0));
+  const size_t e1 = (size_t)b * n, e2 = (size_t)b * m;
+
+  t_ready_arm.flags = A.d_ready;
+  t_ready_arm.per = per;
+  t_ready_arm.abort_word = A.d_abort;
+  const int rc = f.mirror ? nn_distance_fwd_mirrored(b, n, m, f.d_x1, f.d_x2, f.d_d1, f.d_i1, f.d_d2, f.d_i2, f.dist1,
+                                                     f.idx1, f.dist2, f.idx2, mode, (ga_stream_t)sk)
+                          : ga_nn_distance_fwd(b, n, m, f.d_x1, f.d_x2, f.d_d1, f.d_i1, f.d_d2, f.d_i2, mode,
+                                               (ga_stream_t)sk);
+  t_ready_arm.flags = nullptr;
+  GA_TRY(rc);
+  GA_CUDA_TRY(cudaEventRecord(ev_f, sk));
+
+  for (int g = 0; g < groups; g++) {
+    const int b0 = g * per, b1 = b0 + per < b ? b0 + per : b;
+    const size_t o1 = (size_t)b0 * n, o2 = (size_t)b0 * m, c1 = (size_t)(b1 - b0) * n, c2 = (size_t)(b1 - b0) * m;
+    GA_CUDA_TRY(cudaMemcpyAsync(f.d_x1 + o1 * 3, f.xyz1 + o1 * 3, c1 * 12, cudaMemcpyHostToDevice, sin));
+    GA_CUDA_TRY(cudaMemcpyAsync(f.d_x2 + o2 * 3, f.xyz2 + o2 * 3, c2 * 12, cudaMemcpyHostToDevice, sin));
+    GA_CUDA_TRY(cudaMemcpyAsync(A.d_ready + g, A.h_one, sizeof(int), cudaMemcpyHostToDevice, sin));
+  }
+  GA_CUDA_TRY(cudaMemcpyAsync(f.d_g1, f.gd1, e1 * 4, cudaMemcpyHostToDevice, sin));
+  GA_CUDA_TRY(cudaMemcpyAsync(f.d_g2, f.gd2, e2 * 4, cudaMemcpyHostToDevice, sin));
+  GA_CUDA_TRY(cudaEventRecord(ev_g, sin));
+
+  GA_CUDA_TRY(cudaStreamWaitEvent(sk, ev_g, 0));
+  GA_TRY(ga_nn_distance_bwd(b, n, m, f.d_x1, f.d_x2, f.d_g1, f.d_i1, f.d_g2, f.d_i2, f.d_o1, f.d_o2, (ga_stream_t)sk));
+  GA_CUDA_TRY(cudaEventRecord(ev_b, sk));
+
+  if (!f.mirror && (f.dist1 || f.idx1 || f.dist2 || f.idx2)) {
+    GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_f, 0));
+    if (f.dist1) GA_CUDA_TRY(cudaMemcpyAsync(f.dist1, f.d_d1, e1 * 4, cudaMemcpyDeviceToHost, sout));
+    if (f.idx1) GA_CUDA_TRY(cudaMemcpyAsync(f.idx1, f.d_i1, e1 * 4, cudaMemcpyDeviceToHost, sout));
+    if (f.dist2) GA_CUDA_TRY(cudaMemcpyAsync(f.dist2, f.d_d2, e2 * 4, cudaMemcpyDeviceToHost, sout));
+    if (f.idx2) GA_CUDA_TRY(cudaMemcpyAsync(f.idx2, f.d_i2, e2 * 4, cudaMemcpyDeviceToHost, sout));
+  }
+  GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_b, 0));
+  GA_CUDA_TRY(cudaMemcpyAsync(f.gx1, f.d_o1, e1 * 12, cudaMemcpyDeviceToHost, sout));
+  GA_CUDA_TRY(cudaMemcpyAsync(f.gx2, f.d_o2, e2 * 12, cudaMemcpyDeviceToHost, sout));
+  GA_CUDA_TRY(cudaEventRecord(join, sout));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sin, join, 0));
+  return GA_OK;
+}
 
 static int pipeline_lanes(int nchunk) {
   Arena& A = t_arena;
@@ -262,12 +354,16 @@ static int issue_pipeline(const FwdBwdBufs& f, int b, int n, int m, int mode, in
   return GA_OK;
 }
 
-static int capture_pipeline(HostGraph& G, const FwdBwdBufs& f, int b, int n, int m, int mode, int nchunk) {
+// groups > 0: the streamed pipeline with that many arrival groups (nchunk is 1 then).
+static int capture_pipeline(HostGraph& G, const FwdBwdBufs& f, int b, int n, int m, int mode, int nchunk,
+                            int groups = 0) {
   GA_TRY(pipeline_lanes(nchunk));
+  if (groups > 0) GA_TRY(stream_buffers());
   cudaStream_t s0 = t_arena.stream;
   const long long l0 = launch_count_now();
   GA_CUDA_TRY(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
-  const int rc = issue_pipeline(f, b, n, m, mode, nchunk);
+  const int rc = groups > 0 ? issue_pipeline_streamed(f, b, n, m, mode, groups) : issue_pipeline(f, b, n, m, mode, nchunk);
+  t_ready_arm.flags = nullptr;
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(s0, &graph);
   if (rc != GA_OK || e != cudaSuccess || graph == nullptr) {
@@ -286,6 +382,7 @@ static int capture_pipeline(HostGraph& G, const FwdBwdBufs& f, int b, int n, int
   G.launches = (int)(launch_count_now() - l0);
   count_launch(-G.launches);  // counted at capture, but nothing ran yet: replays count below
   G.nchunk = nchunk;
+  G.streamed = groups > 0;
   return GA_OK;
 }
 
@@ -463,22 +560,44 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
         int nc = g_host_graph_chunks > 0 ? g_host_graph_chunks : (traffic >= ((size_t)4 << 20) ? 2 : 1);
         nc = nc < 1 ? 1 : (nc > 8 ? 8 : nc);
         if (nc > b) nc = b;
-        // Small steps (one chunk): the forward kernel writes dist/idx straight into the pinned host buffers
-        // while it searches, which saves four copy nodes (B=10: 92 -> 81 us).  From 4 MB on the posted
-        // PCIe writes slow the kernel more than the copies cost (B=50: 208 vs 216 us, B=200: 575 vs 657).
-        const bool mirror = (g_host_graph_mirror == 2 || (g_host_graph_mirror == 0 && traffic < ((size_t)4 << 20))) &&
+        // The forward kernel writes dist/idx straight into the pinned host buffers while it searches, which saves
+        // four copy nodes per chunk and keeps the D2H engine free for the gradients.  Since the kernel stores whole
+        // 128-byte lines (mma_write) the posted PCIe writes no longer slow it down at any size (profiles/
+        // r02_tune_e2e.txt: B=10 83 vs 96 us with copies, B=50 183 vs 213, B=200 527 vs 578; with the old
+        // 32-byte pieces B=50 was 212 vs 212 and B=200 lost).
+        const bool mirror = (g_host_graph_mirror == 2 || g_host_graph_mirror == 0) &&
                             dist1 && idx1 && dist2 && idx2 && device_can_touch(dist1) && device_can_touch(idx1) &&
                             device_can_touch(dist2) && device_can_touch(idx2);
         FwdBwdBufs f = {xyz1, xyz2, grad_dist1, grad_dist2, dist1, dist2, grad_xyz1, grad_xyz2, idx1, idx2,
                         d_x1, d_x2, d_g1, d_g2, d_d1, d_d2, d_o1, d_o2, d_i1, d_i2, mirror};
-        if (capture_pipeline(G, f, b, n, m, mode, nc) != GA_OK) G.failed = true;  // fall through to the direct path
+        // Streamed ingest (issue_pipeline_streamed), opt-in (key 26 = number of arrival groups).  It works, and it
+        // does not pay on this platform: every copy node of a captured chain costs ~4 us before its first byte
+        // moves, and a group needs three (profiles/r02_tune_e2e.txt, B=50, dist/idx mirrored: one group 185 us,
+        // two 205, four 227, eight 297, against 183 for the two-chunk pipeline above).
+        int groups = 0;
+        if (g_host_stream > 0 && !G.no_stream && fwd_ready_supported(b, n, m)) {
+          groups = g_host_stream;
+          if (groups > kMaxReadyGroups) groups = kMaxReadyGroups;
+          if (groups > b) groups = b;
+        }
+        if (capture_pipeline(G, f, b, n, m, mode, groups > 0 ? 1 : nc, groups) != GA_OK) G.failed = true;  // direct path
       }
     }
+    t_last_streamed = 0;
     if (G.exec != nullptr) {
       GA_CUDA_TRY(cudaGraphLaunch(G.exec, st));
       count_launch(G.launches);
       GA_CUDA_TRY(cudaStreamSynchronize(st));
-      return GA_OK;
+      t_last_streamed = G.streamed ? 1 : 0;
+      if (!(G.streamed && *reinterpret_cast<volatile int*>(t_arena.h_abort) != 0)) return GA_OK;
+      // A CTA gave up waiting for its clouds (wait_ready): the step's results are incomplete.  Drop the graph, keep
+      // this key off the streamed pipeline, and redo the step on the direct path below.
+      *reinterpret_cast<volatile int*>(t_arena.h_abort) = 0;
+      cudaGraphExecDestroy(G.exec);
+      G.exec = nullptr;
+      G.streamed = false;
+      G.no_stream = true;
+      t_last_streamed = -1;
     }
   }
   // Batch elements are independent: split the batch into chunks that alternate between two
@@ -569,6 +688,10 @@ int ga_knn_dists_host(int b, int n, int k, const float* pc, float* out) {
   return GA_OK;
 }
 
+
+// 1 if the calling thread's last ga_nn_distance_fwd_bwd_host replayed the streamed pipeline, -1 if that replay gave
+// up waiting and the step was redone on the direct path, 0 otherwise (tests, tools/tune_e2e.py)
+int ga_debug_host_streamed(void) { return t_last_streamed; }
 
 // development hooks (tools/diag_e2e.py): the two zero-copy building blocks on a caller stream
 int ga_debug_ingest(const void* src, void* dst, size_t bytes, ga_stream_t stream) {

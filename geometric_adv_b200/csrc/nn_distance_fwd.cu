@@ -294,6 +294,17 @@ static bool prefer_umma(int b, int n, int m) {
   return t_umma + 0.5 < t_hmma;
 }
 
+// Streamed ingest is honoured by the HMMA grid kernel only: true if the default dispatch takes that kernel for
+// this shape (same conditions as below) and the clouds are whole 128-byte lines.
+bool fwd_ready_supported(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0 || (n & 31) || (m & 31)) return false;
+  if (g_fwd_variant != 0 && g_fwd_variant != 20) return false;
+  const bool mma_ok = g_fwd_split <= 0 && n >= 256 && m >= 256 &&
+                      (long long)b * ((n + 511) / 512 + (m + 511) / 512) >= 74;
+  if (!mma_ok) return false;
+  return g_fwd_variant == 20 || !(g_umma_auto && prefer_umma(b, n, m));
+}
+
 }  // namespace ga
 
 namespace ga {
@@ -328,6 +339,12 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
   a.mdist1 = mdist1; a.midx1 = midx1; a.mdist2 = mdist2; a.midx2 = midx2;
   a.ticket = nullptr; a.call_id = 0; a.ticket_debug = 0; a.frame_hint = nullptr;
   last_forward().call_id = 0;  // only a ticketed launch below re-arms the gradient kernel's early start
+  if (t_ready_arm.flags != nullptr) {  // streamed ingest (host_api.cu checked fwd_ready_supported)
+    a.ready = t_ready_arm.flags;
+    a.ready_per = t_ready_arm.per;
+    a.ready_abort = t_ready_arm.abort_word;
+    return launch_fwd_mma(a, mode, st);
+  }
   // Default: 4 queries per thread (FMA-pipe bound scan).  Small problems (few hundred query
   // tiles, e.g. the B=1 calls of autoencoder.py:150-168) take 2 queries per thread instead:
   // twice the CTAs to spread over the 148 SMs matters more than the LDS-bound inner loop.

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, MINB) nn_fwd_mma_kernel(const F
   const int nt = rev ? a.n : a.m;
   const float* qpts = (rev ? a.xyz2 : a.xyz1) + (size_t)batch * nq * 3;
   const float* tpts = (rev ? a.xyz1 : a.xyz2) + (size_t)batch * nt * 3;
+  if (!wait_ready(a, batch)) return;  // streamed ingest: this batch element's clouds are on the device from here on
 
   const int qbase = qtile * QT + warp * kMmaQW;  // first query of this warp
   MmaRows R;
@@ -577,6 +578,7 @@ int g_frame = 2;
 std::atomic<int> g_frame_clear{0};  // set by ga_set_tuning(25, .): the next launch clears the device's report
 int g_tickets = 1;  // tuning hook (key 18): 0 = never, 1 = for ga_nn_distance_fwd_bwd only, 2 = always + debug stamps, 3 = always
 thread_local int t_want_tickets = 0;  // set by ga_nn_distance_fwd_bwd around its forward launch
+thread_local ReadyArm t_ready_arm = {nullptr, 1, nullptr};  // set by host_api.cu around a streamed forward launch
 int g_mma_cfg = 0;  // tuning hook (key 7): 0 auto (= 5); 1-5 = (warps, chunk, CTAs/SM) combinations below
 
 template <class Cfg, int MINB>

@@ -28,7 +28,43 @@ struct FwdArgs {
   unsigned long long call_id;
   int ticket_debug;
   int* frame_hint;  // device view of the launcher's off-origin hint word (nn_distance_fwd_mma.cu), or nullptr
+  // Streamed ingest (nn_fwd_mma_kernel only; nullptr = off, see wait_ready below): the clouds are still arriving
+  // over PCIe when the kernel starts; ready[batch / ready_per] turns non-zero once the copy engine has delivered
+  // that group of batch elements.
+  const int* ready = nullptr;
+  int ready_per = 1;
+  int* ready_abort = nullptr;  // set to 1 (mapped host word) by a CTA that gave up waiting
 };
+
+// Streamed ingest, device side.  The host entry (host_api.cu) launches the search on one graph branch and the
+// H2D copies on another: xyz1 / xyz2 arrive in groups of batch elements, each group followed by a 4-byte copy
+// that sets its flag.  A CTA waits for the flag of its batch element before it touches the clouds (one thread
+// polls with a system-scope acquire load, the others sit at the barrier), so the search of group g runs under
+// the copy of group g+1 without splitting the launch.  Copy engines need no SM, hence nothing a waiting CTA
+// holds can delay the data it waits for; should the flag still not come (a driver that serialises the two
+// branches), the CTA gives up after `kReadySpinNs`, raises ready_abort and returns WITHOUT results: the host
+// entry sees the word after the step and redoes the step on the plain path.  Clouds must be whole 128-byte
+// lines (n, m multiples of 32): a line shared by two batch elements could be cached before its second half
+// has arrived.  Returns false if the CTA must leave.  Every thread of the CTA calls it.
+constexpr unsigned long long kReadySpinNs = 4000000ull;
+__device__ __forceinline__ bool wait_ready(const FwdArgs& a, int batch) {
+  if (a.ready == nullptr) return true;
+  __shared__ int ready_ok;
+  if (threadIdx.x == 0) {
+    const int* f = a.ready + batch / a.ready_per;
+    const unsigned long long t0 = global_ns();
+    int v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v != 0 || global_ns() - t0 > kReadySpinNs) break;
+      __nanosleep(200);
+    }
+    if (v == 0) *reinterpret_cast<volatile int*>(a.ready_abort) = 1;
+    ready_ok = v != 0;
+  }
+  __syncthreads();
+  return ready_ok != 0;
+}
 
 template <int THREADS, int Q, int T, int CH>
 struct FwdCfg {

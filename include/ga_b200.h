@@ -224,6 +224,10 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  *      keeps away from the origin (nn_fwd_mma_kernel<frame>); 2 = the plain kernel until one of its launches on the
  *      device has met such a cloud (it reports through a word of mapped host memory, read without synchronisation at
  *      the next launch), the frame kernel from then on; setting the key clears the report.
+ *   26 streamed ingest of the replayed host step (0 = off): n > 0 = the clouds arrive in n groups of batch elements,
+ *      the search starts with the first H2D copy and its CTAs wait, per batch element, for a flag the copy lane raises
+ *      behind each group (where the forward launch is the HMMA grid kernel and n, m are multiples of 32).  Bit-exact;
+ *      not faster than the chunked pipeline on the measured platform (~4 us per copy node), hence opt-in.
  * Clouds far from the origin (relative to their size): the filters' windows scale with (max|q_c| + max|t_c|)^2 measured
  * from the origin of the frame they are evaluated in, so a unit cube at offset 10 costs the plain tensor-core forward
  * 569 us instead of 57 (B=50, 2048 points); the frame kernel takes 63.5 us at any offset, and 57 on centred clouds
@@ -231,6 +235,9 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  * is a plain one; a captured graph keeps the kernel chosen at capture time (set key 25 = 1 before capturing if the
  * clouds are known to sit away from the origin).  The fp32-filter kernels, kNN and all-pairs keep the origin frame. */
 int ga_set_tuning(int key, int value);
+/* 1 if the calling thread's last ga_nn_distance_fwd_bwd_host call replayed the streamed pipeline (key 26), -1 if that
+ * replay gave up waiting for its inputs and the step was redone on the direct path, 0 otherwise. */
+int ga_debug_host_streamed(void);
 /* Empty-kernel launch floor in microseconds (average over `reps` launches). */
 int ga_probe_launch_floor(int reps, float* us, ga_stream_t stream);
 /* Name of the kernel the calling thread launched last through this library ("" before the

@@ -305,6 +305,70 @@ def test_fwd_bwd_host_graph_replay(ga, chunks):
         lib.ga_set_tuning(11, 0)
 
 
+@pytest.mark.parametrize("mirror", [1, 2])
+@pytest.mark.parametrize("groups", [1, 3, 7, 32])
+def test_fwd_bwd_host_streamed_ingest(ga, groups, mirror):
+    """Streamed ingest of the replayed host step (tuning key 26): the search starts with the first H2D copy and
+    its CTAs wait per batch element for the arrival flag of their group.  Fresh contents every step, several
+    shapes, both ways of returning dist/idx; results must be the bits of the device entry points, and the replay
+    must really have been the streamed pipeline (never the give-up path)."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    lib.ga_debug_host_streamed.restype = ctypes.c_int
+    p = ctypes.c_void_p
+    lib.ga_set_tuning(26, groups)
+    lib.ga_set_tuning(17, mirror)
+    lib.ga_set_tuning(0, 20)   # the HMMA grid kernel at every shape below (the automatic choice may be the tcgen05 kernel)
+    try:
+        for (b, n, m) in [(50, 2048, 2048), (48, 2048, 1024), (60, 1024, 2048), (40, 2048, 2016)]:
+            buf = [torch.empty(b, n, 3).pin_memory(), torch.empty(b, m, 3).pin_memory(), torch.empty(b, n).pin_memory(),
+                   torch.empty(b, m).pin_memory(), torch.empty(b, n).pin_memory(),
+                   torch.empty(b, n, dtype=torch.int32).pin_memory(), torch.empty(b, m).pin_memory(),
+                   torch.empty(b, m, dtype=torch.int32).pin_memory(), torch.empty(b, n, 3).pin_memory(),
+                   torch.empty(b, m, 3).pin_memory()]
+            streamed = []
+            for it in range(5):
+                seed = 40 + 7 * it + b
+                a, c = cloud(seed, (b, n, 3)), cloud(seed + 1, (b, m, 3))
+                gd1 = np.random.default_rng(seed).standard_normal((b, n)).astype(np.float32)
+                gd2 = np.random.default_rng(seed + 1).standard_normal((b, m)).astype(np.float32)
+                for dst, src in zip(buf[:4], (a, c, gd1, gd2)):
+                    dst.copy_(torch.from_numpy(src))
+                for o in buf[4:]:
+                    o.zero_()
+                _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, *[p(x.data_ptr()) for x in buf], 0))
+                streamed.append(lib.ga_debug_host_streamed())
+                dev = ga.nn_distance(t(a), t(c))
+                g = ga.nn_distance_grad(t(a), t(c), t(gd1), dev[1], t(gd2), dev[3])
+                for x, y in zip(buf[4:], tuple(dev) + tuple(g)):
+                    assert bits_equal(x.numpy(), y.cpu().numpy()), (b, n, m, it, groups, mirror)
+            assert streamed[0] == 0 and all(v == 1 for v in streamed[2:]), (b, n, m, streamed)
+    finally:
+        lib.ga_set_tuning(26, 0)
+        lib.ga_set_tuning(17, 0)
+        lib.ga_set_tuning(0, 0)
+
+
+def test_fwd_bwd_host_streamed_ingest_not_for_ragged_lines(ga):
+    """Clouds that are not whole 128-byte lines (m = 2000) and launches that do not take the HMMA grid kernel
+    (B = 10: tcgen05 kernel) stay on the chunked pipeline."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    lib.ga_debug_host_streamed.restype = ctypes.c_int
+    p = ctypes.c_void_p
+    lib.ga_set_tuning(26, 4)
+    for (b, n, m) in [(24, 2048, 2000), (10, 2048, 2048)]:
+        buf = [torch.rand(b, n, 3).pin_memory(), torch.rand(b, m, 3).pin_memory(), torch.rand(b, n).pin_memory(),
+               torch.rand(b, m).pin_memory(), torch.empty(b, n).pin_memory(),
+               torch.empty(b, n, dtype=torch.int32).pin_memory(), torch.empty(b, m).pin_memory(),
+               torch.empty(b, m, dtype=torch.int32).pin_memory(), torch.empty(b, n, 3).pin_memory(),
+               torch.empty(b, m, 3).pin_memory()]
+        for it in range(3):
+            _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, *[p(x.data_ptr()) for x in buf], 0))
+            assert lib.ga_debug_host_streamed() == 0
+    lib.ga_set_tuning(26, 0)
+
+
 @pytest.mark.parametrize("shape", [(50, 2048, 2048), (37, 2048, 2000), (10, 2048, 2048), (3, 300, 257), (12, 1000, 4000)])
 def test_fused_device_entry_equals_separate_calls(ga, shape):
     """ga_nn_distance_fwd_bwd: gradient CTAs start per batch element behind the search's completion tickets

@@ -30,11 +30,16 @@ for (B, N, M) in [(50, 2048, 2048), (10, 2048, 2048), (200, 2048, 2048)]:
 
     key = "b%d" % B
     out[key] = {}
-    for name, k10, k11, k17 in ([("direct", 1, 0, 0)] + [("graph_c%d_mirror_dist_idx" % c, 0, c, 2) for c in (1, 2, 3, 4)] +
-                                [("graph_c%d_copy_dist_idx" % c, 0, c, 1) for c in (1, 2, 3)] + [("graph_auto", 0, 0, 0)]):
+    for name, k10, k11, k17, k26 in ([("direct", 1, 0, 0, -1)] +
+                                     [("graph_c%d_mirror_dist_idx" % c, 0, c, 2, -1) for c in (1, 2)] +
+                                     [("graph_c%d_copy_dist_idx" % c, 0, c, 1, -1) for c in (1, 2, 3)] +
+                                     [("streamed_g%d_mirror_dist_idx" % g, 0, 0, 2, g) for g in (1, 2, 3, 4, 5, 6, 8, 12)] +
+                                     [("streamed_g%d_copy_dist_idx" % g, 0, 0, 1, g) for g in (1, 2, 3, 4, 5, 6, 8, 12)] +
+                                     [("graph_auto", 0, 0, 0, 0)]):
         lib.ga_set_tuning(10, k10)
         lib.ga_set_tuning(11, k11)
         lib.ga_set_tuning(17, k17)
+        lib.ga_set_tuning(26, k26)
         for _ in range(5):
             step()
         ts = []
@@ -44,9 +49,12 @@ for (B, N, M) in [(50, 2048, 2048), (10, 2048, 2048), (200, 2048, 2048)]:
             ts.append(time.perf_counter() - t0)
         ts.sort()
         out[key][name] = {"min_us": ts[0] * 1e6, "med_us": ts[len(ts) // 2] * 1e6}
-        print(key, name, "min %.1f us  med %.1f us" % (ts[0] * 1e6, ts[len(ts) // 2] * 1e6), flush=True)
+        out[key][name]["streamed"] = lib.ga_debug_host_streamed()
+        print(key, name, "min %.1f us  med %.1f us  streamed %d" % (ts[0] * 1e6, ts[len(ts) // 2] * 1e6,
+                                                                     out[key][name]["streamed"]), flush=True)
     lib.ga_set_tuning(10, 0)
     lib.ga_set_tuning(11, 0)
     lib.ga_set_tuning(17, 0)
+    lib.ga_set_tuning(26, 0)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune_e2e.json"), "w"), indent=1)
