@@ -37,6 +37,7 @@ struct ReadyArm {
   const int* flags;
   int per;
   int* abort_word;
+  int pdl;  // launch the forward as a programmatic dependent of the kernel before it (the SM-driven ingest)
 };
 extern thread_local ReadyArm t_ready_arm;                // nn_distance_fwd_mma.cu
 bool fwd_ready_supported(int b, int n, int m);          // nn_distance_fwd.cu: would that launch honour the flags?

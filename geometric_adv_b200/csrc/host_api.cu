@@ -139,6 +139,48 @@ __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
   }
 }
 
+// Streamed ingest by the SMs (issue_pipeline_pulled): a few CTAs pull the clouds of one batch element after the other
+// out of the caller's pinned buffers (16-byte loads over PCIe, all of an element's loads of a thread in flight at
+// once) and raise that element's arrival flag; the forward kernel, launched behind this one as a programmatic
+// dependent (it starts as soon as every CTA here has passed the trigger below, and never waits for the grid), has
+// its CTAs wait per batch element (wait_ready, nn_search.cuh).  No copy node, no per-group overhead: the search of
+// element e runs under the transfer of the elements behind it.  v1 / v2: 16-byte vectors per cloud of a batch element.
+struct PullArgs {
+  const int4* src1;
+  const int4* src2;
+  int4* dst1;
+  int4* dst2;
+  int* ready;
+  int b, v1, v2;
+};
+
+__global__ void __launch_bounds__(256) ingest_stream_kernel(const PullArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  constexpr int U = 6;  // vectors in flight per thread and round (256 threads x 6 x 16 B = one 2048-point cloud)
+  for (int e = blockIdx.x; e < a.b; e += gridDim.x) {
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+      const int nv = c ? a.v2 : a.v1;
+      const int4* src = (c ? a.src2 : a.src1) + (size_t)e * nv;
+      int4* dst = (c ? a.dst2 : a.dst1) + (size_t)e * nv;
+      for (int i0 = threadIdx.x; i0 < nv; i0 += 256 * U) {
+        int4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (i0 + u * 256 < nv) v[u] = src[i0 + u * 256];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (i0 + u * 256 < nv) dst[i0 + u * 256] = v[u];
+      }
+    }
+    __syncthreads();  // every thread's stores are issued ...
+    if (threadIdx.x == 0) {
+      __threadfence();  // ... and ordered before the flag (cumulative over the barrier)
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ready + e), "r"(1) : "memory");
+    }
+  }
+}
+
 int g_host_chunks = 0;  // tuning hook (key 3): force the chunk count of the copy path
 int g_host_path = 0;  // tuning hook (ga_set_tuning key 2): 0 auto, 1 force copies, 2 force zero-copy
 
@@ -174,6 +216,7 @@ static bool device_can_touch(const void* p) {
 int g_host_graph = 0;         // tuning hook (key 10): 0 auto, 1 never replay, 2 capture on first sight
 int g_host_graph_chunks = 0;  // tuning hook (key 11): chunks of the captured pipeline (0 = auto)
 int g_host_graph_epoch = 0;   // bumped by ga_set_tuning(10 | 11 | 17): cached graphs of older epochs are dropped
+int g_host_pull = 0;          // tuning hook (key 27): clouds pulled by the SMs behind arrival flags: 0 auto, -1 off, n = ingest CTAs
 int g_host_stream = 0;        // tuning hook (key 26): streamed ingest of the replayed step: 0 off, n = arrival groups
 int g_host_graph_mirror = 0;  // tuning hook (key 17): 0 auto, 1 = always copy dist/idx, 2 = always let the forward
                               // kernel write them straight to the pinned host buffers inside the replayed graph
@@ -212,11 +255,12 @@ struct FwdBwdBufs {
 };
 
 constexpr int kMaxReadyGroups = 32;
+constexpr int kMaxReadyElems = 16384;  // arrival flags of the pulled pipeline: one per batch element
 
 // Buffers of the streamed pipeline; called outside any capture.
 static int stream_buffers() {
   Arena& A = t_arena;
-  if (!A.d_ready) GA_CUDA_TRY(cudaMalloc(&A.d_ready, sizeof(int) * kMaxReadyGroups));
+  if (!A.d_ready) GA_CUDA_TRY(cudaMalloc(&A.d_ready, sizeof(int) * kMaxReadyElems));
   if (!A.h_one) {
     GA_CUDA_TRY(cudaHostAlloc(&A.h_one, sizeof(int), cudaHostAllocDefault));
     *A.h_one = 1;
@@ -354,16 +398,81 @@ static int issue_pipeline(const FwdBwdBufs& f, int b, int n, int m, int mode, in
   return GA_OK;
 }
 
-// groups > 0: the streamed pipeline with that many arrival groups (nchunk is 1 then).
+// The step with the clouds pulled by the SMs (ingest_stream_kernel): kernel lane = ingest -> forward (programmatic
+// dependent, waits per batch element) -> backward; the upstream gradients come by DMA on the copy-in lane meanwhile;
+// gradients (and dist/idx unless mirrored) leave on the out lane as in issue_pipeline.  ctas = ingest CTAs.
+static int issue_pipeline_pulled(const FwdBwdBufs& f, int b, int n, int m, int mode, int ctas) {
+  Arena& A = t_arena;
+  cudaStream_t sin = A.stream, sout = A.out_lane, sk = A.k_lane[0];
+  cudaEvent_t fork = A.ev[0], join = A.ev[1], ev_g = A.ev[10], ev_f = A.ev[18], ev_b = A.ev[26];
+  const size_t e1 = (size_t)b * n, e2 = (size_t)b * m;
+  GA_CUDA_TRY(cudaMemsetAsync(A.d_ready, 0, sizeof(int) * b, sin));
+  GA_CUDA_TRY(cudaEventRecord(fork, sin));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sout, fork, 0));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sk, fork, 0));
+
+  PullArgs pa;
+  pa.src1 = reinterpret_cast<const int4*>(f.xyz1);
+  pa.src2 = reinterpret_cast<const int4*>(f.xyz2);
+  pa.dst1 = reinterpret_cast<int4*>(f.d_x1);
+  pa.dst2 = reinterpret_cast<int4*>(f.d_x2);
+  pa.ready = A.d_ready;
+  pa.b = b;
+  pa.v1 = n * 12 / 16;
+  pa.v2 = m * 12 / 16;
+  ingest_stream_kernel<<<ctas < b ? ctas : b, 256, 0, sk>>>(pa);
+  GA_LAUNCH_CHECK("ingest_stream_kernel");
+
+  t_ready_arm.flags = A.d_ready;
+  t_ready_arm.per = 1;
+  t_ready_arm.abort_word = A.d_abort;
+  t_ready_arm.pdl = 1;
+  const int rc = f.mirror ? nn_distance_fwd_mirrored(b, n, m, f.d_x1, f.d_x2, f.d_d1, f.d_i1, f.d_d2, f.d_i2, f.dist1,
+                                                     f.idx1, f.dist2, f.idx2, mode, (ga_stream_t)sk)
+                          : ga_nn_distance_fwd(b, n, m, f.d_x1, f.d_x2, f.d_d1, f.d_i1, f.d_d2, f.d_i2, mode,
+                                               (ga_stream_t)sk);
+  t_ready_arm.flags = nullptr;
+  t_ready_arm.pdl = 0;
+  GA_TRY(rc);
+  GA_CUDA_TRY(cudaEventRecord(ev_f, sk));
+
+  GA_CUDA_TRY(cudaMemcpyAsync(f.d_g1, f.gd1, e1 * 4, cudaMemcpyHostToDevice, sin));
+  GA_CUDA_TRY(cudaMemcpyAsync(f.d_g2, f.gd2, e2 * 4, cudaMemcpyHostToDevice, sin));
+  GA_CUDA_TRY(cudaEventRecord(ev_g, sin));
+
+  GA_CUDA_TRY(cudaStreamWaitEvent(sk, ev_g, 0));
+  GA_TRY(ga_nn_distance_bwd(b, n, m, f.d_x1, f.d_x2, f.d_g1, f.d_i1, f.d_g2, f.d_i2, f.d_o1, f.d_o2, (ga_stream_t)sk));
+  GA_CUDA_TRY(cudaEventRecord(ev_b, sk));
+
+  if (!f.mirror && (f.dist1 || f.idx1 || f.dist2 || f.idx2)) {
+    GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_f, 0));
+    if (f.dist1) GA_CUDA_TRY(cudaMemcpyAsync(f.dist1, f.d_d1, e1 * 4, cudaMemcpyDeviceToHost, sout));
+    if (f.idx1) GA_CUDA_TRY(cudaMemcpyAsync(f.idx1, f.d_i1, e1 * 4, cudaMemcpyDeviceToHost, sout));
+    if (f.dist2) GA_CUDA_TRY(cudaMemcpyAsync(f.dist2, f.d_d2, e2 * 4, cudaMemcpyDeviceToHost, sout));
+    if (f.idx2) GA_CUDA_TRY(cudaMemcpyAsync(f.idx2, f.d_i2, e2 * 4, cudaMemcpyDeviceToHost, sout));
+  }
+  GA_CUDA_TRY(cudaStreamWaitEvent(sout, ev_b, 0));
+  GA_CUDA_TRY(cudaMemcpyAsync(f.gx1, f.d_o1, e1 * 12, cudaMemcpyDeviceToHost, sout));
+  GA_CUDA_TRY(cudaMemcpyAsync(f.gx2, f.d_o2, e2 * 12, cudaMemcpyDeviceToHost, sout));
+  GA_CUDA_TRY(cudaEventRecord(join, sout));
+  GA_CUDA_TRY(cudaStreamWaitEvent(sin, join, 0));
+  return GA_OK;
+}
+
+// groups > 0: the streamed pipeline with that many arrival groups (nchunk is 1 then); groups < 0: the pulled pipeline
+// with -groups ingest CTAs.
 static int capture_pipeline(HostGraph& G, const FwdBwdBufs& f, int b, int n, int m, int mode, int nchunk,
                             int groups = 0) {
   GA_TRY(pipeline_lanes(nchunk));
-  if (groups > 0) GA_TRY(stream_buffers());
+  if (groups != 0) GA_TRY(stream_buffers());
   cudaStream_t s0 = t_arena.stream;
   const long long l0 = launch_count_now();
   GA_CUDA_TRY(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
-  const int rc = groups > 0 ? issue_pipeline_streamed(f, b, n, m, mode, groups) : issue_pipeline(f, b, n, m, mode, nchunk);
+  const int rc = groups > 0   ? issue_pipeline_streamed(f, b, n, m, mode, groups)
+                 : groups < 0 ? issue_pipeline_pulled(f, b, n, m, mode, -groups)
+                              : issue_pipeline(f, b, n, m, mode, nchunk);
   t_ready_arm.flags = nullptr;
+  t_ready_arm.pdl = 0;
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(s0, &graph);
   if (rc != GA_OK || e != cudaSuccess || graph == nullptr) {
@@ -382,7 +491,7 @@ static int capture_pipeline(HostGraph& G, const FwdBwdBufs& f, int b, int n, int
   G.launches = (int)(launch_count_now() - l0);
   count_launch(-G.launches);  // counted at capture, but nothing ran yet: replays count below
   G.nchunk = nchunk;
-  G.streamed = groups > 0;
+  G.streamed = groups != 0;
   return GA_OK;
 }
 
@@ -580,7 +689,17 @@ int ga_nn_distance_fwd_bwd_host(int b, int n, int m, const float* xyz1, const fl
           if (groups > kMaxReadyGroups) groups = kMaxReadyGroups;
           if (groups > b) groups = b;
         }
-        if (capture_pipeline(G, f, b, n, m, mode, groups > 0 ? 1 : nc, groups) != GA_OK) G.failed = true;  // direct path
+        // Pulled ingest (issue_pipeline_pulled): the clouds come over PCIe by the loads of a few CTAs instead of
+        // copy nodes, one arrival flag per batch element, the search runs under the transfer.  Measured
+        // (profiles/r02_tune_e2e.txt, dist/idx mirrored): B=50 174 us with 8 ingest CTAs (2: 225, 4: 187, 12: 177,
+        // 32: 173, 50: 186) against 183-200 for the two-chunk pipeline; B=200 512 against 529.  Default from 4 MB
+        // of traffic (below that the tcgen05 kernel serves the step and the copies are short); key 27 = -1 turns
+        // it off, n > 0 sets the CTAs.  Needs device-readable, 16-byte aligned clouds.
+        if (g_host_pull >= 0 && groups == 0 && !G.no_stream && b <= kMaxReadyElems && fwd_ready_supported(b, n, m) &&
+            (g_host_pull > 0 || (traffic >= ((size_t)4 << 20) && traffic <= ((size_t)1 << 30))) &&
+            device_can_touch(xyz1) && device_can_touch(xyz2) && ((uintptr_t)xyz1 & 15) == 0 && ((uintptr_t)xyz2 & 15) == 0)
+          groups = -(g_host_pull > 0 ? g_host_pull : 8);
+        if (capture_pipeline(G, f, b, n, m, mode, groups != 0 ? 1 : nc, groups) != GA_OK) G.failed = true;  // direct path
       }
     }
     t_last_streamed = 0;

@@ -343,6 +343,8 @@ int nn_distance_fwd_mirrored(int b, int n, int m, const float* xyz1, const float
     a.ready = t_ready_arm.flags;
     a.ready_per = t_ready_arm.per;
     a.ready_abort = t_ready_arm.abort_word;
+    // patience of a waiting CTA: 4 ms + the whole transfer at 1 GB/s (a twentieth of what the link does)
+    a.ready_spin_us = 4000u + (unsigned)(((long long)b * ((long long)n + m) * 12) / 1000);
     return launch_fwd_mma(a, mode, st);
   }
   // Default: 4 queries per thread (FMA-pipe bound scan).  Small problems (few hundred query

@@ -578,7 +578,7 @@ int g_frame = 2;
 std::atomic<int> g_frame_clear{0};  // set by ga_set_tuning(25, .): the next launch clears the device's report
 int g_tickets = 1;  // tuning hook (key 18): 0 = never, 1 = for ga_nn_distance_fwd_bwd only, 2 = always + debug stamps, 3 = always
 thread_local int t_want_tickets = 0;  // set by ga_nn_distance_fwd_bwd around its forward launch
-thread_local ReadyArm t_ready_arm = {nullptr, 1, nullptr};  // set by host_api.cu around a streamed forward launch
+thread_local ReadyArm t_ready_arm = {nullptr, 1, nullptr, 0};  // set by host_api.cu around a streamed forward launch
 int g_mma_cfg = 0;  // tuning hook (key 7): 0 auto (= 5); 1-5 = (warps, chunk, CTAs/SM) combinations below
 
 template <class Cfg, int MINB>
@@ -627,7 +627,23 @@ static int launch_fwd_mma_cfg(FwdArgs a, int mode, cudaStream_t st) {
     if (a.ticket != nullptr) a.call_id = next_call_id();
   }
   a.ticket_debug = g_tickets == 2;
-  k<<<(unsigned)jobs, Cfg::kThreads, Cfg::kSmem, st>>>(a);
+  if (a.ready != nullptr && t_ready_arm.pdl) {
+    // behind the SM-driven ingest: start as soon as its CTAs are resident (the kernel never waits for that grid;
+    // its CTAs wait for the arrival flags)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)jobs);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    GA_CUDA_TRY(cudaLaunchKernelEx(&cfg, k, a));
+  } else {
+    k<<<(unsigned)jobs, Cfg::kThreads, Cfg::kSmem, st>>>(a);
+  }
   GA_LAUNCH_CHECK(frame ? "nn_fwd_mma_kernel<frame>" : "nn_fwd_mma_kernel");
   if (a.call_id != 0) {
     LastForward& lf = last_forward();

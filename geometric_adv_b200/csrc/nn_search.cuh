@@ -34,6 +34,7 @@ struct FwdArgs {
   const int* ready = nullptr;
   int ready_per = 1;
   int* ready_abort = nullptr;  // set to 1 (mapped host word) by a CTA that gave up waiting
+  unsigned ready_spin_us = 4000;  // how long a CTA waits before it gives up (the launcher scales it with the transfer)
 };
 
 // Streamed ingest, device side.  The host entry (host_api.cu) launches the search on one graph branch and the
@@ -42,11 +43,10 @@ struct FwdArgs {
 // polls with a system-scope acquire load, the others sit at the barrier), so the search of group g runs under
 // the copy of group g+1 without splitting the launch.  Copy engines need no SM, hence nothing a waiting CTA
 // holds can delay the data it waits for; should the flag still not come (a driver that serialises the two
-// branches), the CTA gives up after `kReadySpinNs`, raises ready_abort and returns WITHOUT results: the host
+// branches), the CTA gives up after ready_spin_us, raises ready_abort and returns WITHOUT results: the host
 // entry sees the word after the step and redoes the step on the plain path.  Clouds must be whole 128-byte
 // lines (n, m multiples of 32): a line shared by two batch elements could be cached before its second half
 // has arrived.  Returns false if the CTA must leave.  Every thread of the CTA calls it.
-constexpr unsigned long long kReadySpinNs = 4000000ull;
 __device__ __forceinline__ bool wait_ready(const FwdArgs& a, int batch) {
   if (a.ready == nullptr) return true;
   __shared__ int ready_ok;
@@ -56,7 +56,7 @@ __device__ __forceinline__ bool wait_ready(const FwdArgs& a, int batch) {
     int v;
     for (;;) {
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v != 0 || global_ns() - t0 > kReadySpinNs) break;
+      if (v != 0 || global_ns() - t0 > 1000ull * a.ready_spin_us) break;
       __nanosleep(200);
     }
     if (v == 0) *reinterpret_cast<volatile int*>(a.ready_abort) = 1;

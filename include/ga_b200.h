@@ -228,6 +228,10 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  *      the search starts with the first H2D copy and its CTAs wait, per batch element, for a flag the copy lane raises
  *      behind each group (where the forward launch is the HMMA grid kernel and n, m are multiples of 32).  Bit-exact;
  *      not faster than the chunked pipeline on the measured platform (~4 us per copy node), hence opt-in.
+ *   27 pulled ingest of the replayed host step (0 = auto: 8 CTAs from 4 MB of traffic where the forward launch is the
+ *      HMMA grid kernel, n and m are multiples of 32 and the clouds are device-readable pinned memory; -1 = off;
+ *      n > 0 = that many ingest CTAs): a few CTAs load the clouds over PCIe, one arrival flag per batch element, the
+ *      search starts behind them as a programmatic dependent and runs under the transfer.  Bit-exact.
  * Clouds far from the origin (relative to their size): the filters' windows scale with (max|q_c| + max|t_c|)^2 measured
  * from the origin of the frame they are evaluated in, so a unit cube at offset 10 costs the plain tensor-core forward
  * 569 us instead of 57 (B=50, 2048 points); the frame kernel takes 63.5 us at any offset, and 57 on centred clouds

@@ -306,8 +306,20 @@ def test_fwd_bwd_host_graph_replay(ga, chunks):
 
 
 @pytest.mark.parametrize("mirror", [1, 2])
+@pytest.mark.parametrize("ctas", [1, 8, 40])
+def test_fwd_bwd_host_pulled_ingest(ga, ctas, mirror):
+    """Tuning key 27: the clouds are pulled out of the pinned buffers by a few CTAs (ingest_stream_kernel), one
+    arrival flag per batch element, the search starts behind them as a programmatic dependent.  Same checks."""
+    _streamed_ingest_case(ga, 27, ctas, mirror)
+
+
+@pytest.mark.parametrize("mirror", [1, 2])
 @pytest.mark.parametrize("groups", [1, 3, 7, 32])
 def test_fwd_bwd_host_streamed_ingest(ga, groups, mirror):
+    _streamed_ingest_case(ga, 26, groups, mirror)
+
+
+def _streamed_ingest_case(ga, key, groups, mirror):
     """Streamed ingest of the replayed host step (tuning key 26): the search starts with the first H2D copy and
     its CTAs wait per batch element for the arrival flag of their group.  Fresh contents every step, several
     shapes, both ways of returning dist/idx; results must be the bits of the device entry points, and the replay
@@ -316,7 +328,7 @@ def test_fwd_bwd_host_streamed_ingest(ga, groups, mirror):
     lib = _lib.load()
     lib.ga_debug_host_streamed.restype = ctypes.c_int
     p = ctypes.c_void_p
-    lib.ga_set_tuning(26, groups)
+    lib.ga_set_tuning(key, groups)
     lib.ga_set_tuning(17, mirror)
     lib.ga_set_tuning(0, 20)   # the HMMA grid kernel at every shape below (the automatic choice may be the tcgen05 kernel)
     try:
@@ -344,7 +356,7 @@ def test_fwd_bwd_host_streamed_ingest(ga, groups, mirror):
                     assert bits_equal(x.numpy(), y.cpu().numpy()), (b, n, m, it, groups, mirror)
             assert streamed[0] == 0 and all(v == 1 for v in streamed[2:]), (b, n, m, streamed)
     finally:
-        lib.ga_set_tuning(26, 0)
+        lib.ga_set_tuning(key, 0)
         lib.ga_set_tuning(17, 0)
         lib.ga_set_tuning(0, 0)
 
@@ -357,6 +369,7 @@ def test_fwd_bwd_host_streamed_ingest_not_for_ragged_lines(ga):
     lib.ga_debug_host_streamed.restype = ctypes.c_int
     p = ctypes.c_void_p
     lib.ga_set_tuning(26, 4)
+    lib.ga_set_tuning(27, 8)
     for (b, n, m) in [(24, 2048, 2000), (10, 2048, 2048)]:
         buf = [torch.rand(b, n, 3).pin_memory(), torch.rand(b, m, 3).pin_memory(), torch.rand(b, n).pin_memory(),
                torch.rand(b, m).pin_memory(), torch.empty(b, n).pin_memory(),
@@ -367,6 +380,7 @@ def test_fwd_bwd_host_streamed_ingest_not_for_ragged_lines(ga):
             _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, *[p(x.data_ptr()) for x in buf], 0))
             assert lib.ga_debug_host_streamed() == 0
     lib.ga_set_tuning(26, 0)
+    lib.ga_set_tuning(27, 0)
 
 
 @pytest.mark.parametrize("shape", [(50, 2048, 2048), (37, 2048, 2000), (10, 2048, 2048), (3, 300, 257), (12, 1000, 4000)])

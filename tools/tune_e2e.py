@@ -30,16 +30,18 @@ for (B, N, M) in [(50, 2048, 2048), (10, 2048, 2048), (200, 2048, 2048)]:
 
     key = "b%d" % B
     out[key] = {}
-    for name, k10, k11, k17, k26 in ([("direct", 1, 0, 0, -1)] +
-                                     [("graph_c%d_mirror_dist_idx" % c, 0, c, 2, -1) for c in (1, 2)] +
-                                     [("graph_c%d_copy_dist_idx" % c, 0, c, 1, -1) for c in (1, 2, 3)] +
-                                     [("streamed_g%d_mirror_dist_idx" % g, 0, 0, 2, g) for g in (1, 2, 3, 4, 5, 6, 8, 12)] +
-                                     [("streamed_g%d_copy_dist_idx" % g, 0, 0, 1, g) for g in (1, 2, 3, 4, 5, 6, 8, 12)] +
-                                     [("graph_auto", 0, 0, 0, 0)]):
+    for name, k10, k11, k17, k26, k27 in ([("direct", 1, 0, 0, 0, 0)] +
+                                          [("graph_c%d_mirror_dist_idx" % c, 0, c, 2, 0, 0) for c in (1, 2)] +
+                                          [("graph_c%d_copy_dist_idx" % c, 0, c, 1, 0, 0) for c in (1, 2)] +
+                                          [("streamed_g%d_mirror_dist_idx" % g, 0, 0, 2, g, 0) for g in (1, 2, 4)] +
+                                          [("pulled_c%d_mirror_dist_idx" % c, 0, 0, 2, 0, c) for c in (2, 4, 8, 12, 16, 24, 32, 50)] +
+                                          [("pulled_c%d_copy_dist_idx" % c, 0, 0, 1, 0, c) for c in (8, 16, 32)] +
+                                          [("graph_auto", 0, 0, 0, 0, 0)]):
         lib.ga_set_tuning(10, k10)
         lib.ga_set_tuning(11, k11)
         lib.ga_set_tuning(17, k17)
         lib.ga_set_tuning(26, k26)
+        lib.ga_set_tuning(27, k27)
         for _ in range(5):
             step()
         ts = []
@@ -56,5 +58,6 @@ for (B, N, M) in [(50, 2048, 2048), (10, 2048, 2048), (200, 2048, 2048)]:
     lib.ga_set_tuning(11, 0)
     lib.ga_set_tuning(17, 0)
     lib.ga_set_tuning(26, 0)
+    lib.ga_set_tuning(27, 0)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune_e2e.json"), "w"), indent=1)
