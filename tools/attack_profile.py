@@ -17,8 +17,10 @@ atk.init_pert()
 for _ in range(4):
     atk.step()
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_push("iteration")
+# cudaProfilerStart/Stop around ONE iteration (ncu --profile-from-start off): an NVTX range would miss the kernels
+# the autograd engine launches from its own thread
+torch.cuda.profiler.start()
 atk.step()
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_pop()
+torch.cuda.profiler.stop()
 print("done")
