@@ -43,6 +43,15 @@ def all_gather_rows(block, total_rows, group=None):
     world, rank = _world(group)
     if world == 1:
         return block
+    # NCCL moves bytes of a handful of element types; int16 (the nn_idx stage file's type) and bool are not among
+    # them: gather such blocks as raw bytes and view the result back
+    if block.is_cuda and block.dtype in (torch.int16, torch.bool, torch.uint16):
+        rowbytes = block.element_size()
+        for d in block.shape[1:]:
+            rowbytes *= int(d)
+        flat = block.contiguous().view(torch.uint8).reshape(block.shape[0], rowbytes)
+        out = all_gather_rows(flat, total_rows, group)
+        return out.view(block.dtype).reshape((total_rows,) + tuple(block.shape[1:]))
     sizes = [shard_range(total_rows, world, r) for r in range(world)]
     maxrows = max(hi - lo for lo, hi in sizes)
     if total_rows % world == 0 and block.is_cuda:  # equal blocks: one NCCL all-gather straight into the result
