@@ -549,13 +549,15 @@ def leg_knn(dev, world, rank, fp32_peak, flush, quick):
     t_g = sum(e[1].elapsed_time(e[2]) for e in ev) / reps
     t_all = sum(e[0].elapsed_time(e[2]) for e in ev) / reps
     t_k, t_g, t_all = _max_over_ranks([t_k, t_g, t_all], dev, world)
+    from geometric_adv_b200 import _lib
+    knn_kernel_name = _lib.load().ga_last_kernel().decode()  # knn_slab_kernel for large shards, knn_kernel below
     out = {
         "workload": "configs[4]: kNN per-point distances k=%d, B=%d clouds x %d points over %d GPU(s)" % (KNN_K, b, N, world),
         "scaling": "strong", "ms": t_all, "clouds_per_s": b / (t_all * 1e-3),
         "point_pairs_per_s": b * float(N) * N / (t_all * 1e-3),
         "phases_ms": {"knn_kernel": t_k, "all_gather": t_g}, "gather_share": t_g / t_all,
         "checks": {"ascending": bool((full[:, :, 1:] >= full[:, :, :-1]).all()), "shape": list(full.shape)},
-        "roofline": {"bound": "fp32", "kernel": "knn_kernel", "achieved": 8.0 * (hi - lo) * float(N) * N / (t_k * 1e-3) / 1e12,
+        "roofline": {"bound": "fp32", "kernel": knn_kernel_name, "achieved": 8.0 * (hi - lo) * float(N) * N / (t_k * 1e-3) / 1e12,
                      "peak": fp32_peak, "unit": "TFLOP/s", "ms_per_launch": t_k, "traffic": None},
     }
     out["roofline"]["frac"] = out["roofline"]["achieved"] / fp32_peak

@@ -25,6 +25,7 @@ extern int g_host_graph_epoch;   // host_api.cu
 extern int g_host_graph_mirror;  // host_api.cu
 extern int g_host_stream;        // host_api.cu
 extern int g_host_pull;          // host_api.cu
+extern int g_knn_slab;           // grouping.cu
 extern int g_umma_grid;          // nn_distance_fwd_umma.cu
 extern int g_bwd_stage;          // nn_distance_bwd.cu
 extern int g_bwd_kernel;         // nn_distance_bwd.cu
@@ -290,6 +291,10 @@ int ga_set_tuning(int key, int value) {
   if (key == 25) {
     ga::g_frame = value;
     ga::g_frame_clear.store(1, std::memory_order_relaxed);
+    return GA_OK;
+  }
+  if (key == 28) {
+    ga::g_knn_slab = value;
     return GA_OK;
   }
   if (key == 27) {

@@ -171,8 +171,9 @@ __device__ __forceinline__ void list_insert(float (&Lv)[KL], int (&Li)[KL], floa
   }
 }
 
+// Body of knn_kernel as a device function: knn_slab_kernel (below) runs it for clouds it does not take itself.
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
+__device__ __forceinline__ void knn_body(const KnnArgs& a) {
   constexpr int THREADS = Cfg::kThreads, Q = Cfg::kQ, QT = Cfg::kQT, T = Cfg::kT, CH = Cfg::kCH, KL = Cfg::kKL;
   constexpr bool MULTI = Cfg::kMulti;
   constexpr int LQ = MULTI ? Q : 1;  // persistent lists only when chunks have to be merged
@@ -861,6 +862,515 @@ __global__ void __launch_bounds__(256) group_point_kernel(long long total, int n
 }
 
 template <class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
+  knn_body<Cfg>(a);
+}
+
+// ---- knn_slab_kernel: the defense epilogue's kNN distances (ga_knn_dists) with the scans pruned to an x-slab -------
+//
+// ga_knn_dists returns VALUES only (sqrt of the k+1 smallest squared distances of every point to its own cloud, the
+// first dropped: get_knn_dists_per_point.py:78-81), so neither the order of equal distances nor the identity of the
+// neighbours matters, and the cloud may be reordered.  Per CTA (= cloud, 512 queries) the cloud is counting-sorted
+// by x into 1024 bins (every CTA of a cloud sorts it again: ~2 us against ~15 us of search) and staged in that order;
+// a warp owns 64 queries that are neighbours in the sorted order, i.e. a thin slab [xa, xb] of the cloud.
+//   A0  filter scan (nn_tiles.cuh) over the warp's own positions +- kSlabSeed targets: the K-th smallest minimum
+//       over tiles of 16 targets is tau, K distinct targets with filter value <= tau.  Hence the K-th smallest
+//       exact distance of query j is at most U_j = tau_j + |q_j|^2 + error terms.
+//   r   r^2 >= max_j U_j over the warp.  A target whose x lies outside [xa - r, xb + r] (directed rounding) has
+//       |dx| > r to every query of the warp, so its reference distance fl(dx^2 + ..) >= fl(r^2) > U_j: it is not among
+//       the K smallest of any of them.  The bin of a coordinate is a monotonic function of it, so the targets inside
+//       the window are a contiguous range of the sorted order, found from the bin starts.
+//   B1  second scan over that range only: targets with f <= tau + W (the window of knn_kernel) go to the query's queue;
+//   B2  queued targets in the reference arithmetic into an exact sorted list of K values, written as sqrt.
+// On uniform clouds of 2048 points A0 sees ~19 % and B1 ~35 % of the cloud where knn_kernel scans all of it twice.
+// A query whose queue overflows (dense clusters) is served by the whole warp with K selection passes over the
+// cloud.  A cloud with a non-finite or huge coordinate, or fewer than 512 points, is handed to knn_body unchanged
+// (NaN distances take part in the reference's selection sort in a way only its replay reproduces).
+constexpr int kSlabBins = 1024;
+constexpr int kSlabSeed = 160;
+constexpr int kSlabT = 16;
+constexpr int kSlabMaxBin = 32;  // fullest bin the slab path takes (its points get an insertion sort by index)
+
+using SlabBase = KnnCfg<256, 2, 32, 2048, 12, false>;
+struct SlabCfg {
+  static constexpr int kThreads = 256, kQ = 2, kQT = 512, kCH = 2048, kKL = 12;
+  // tgt (+ pipeline pad) | hist/starts int[1026] | qidx u16[2048] | red[64] | queue u16[(32 + 16)][512]
+  static constexpr size_t kOffHist = (size_t)kCH * 16 + (size_t)kPipeU * 32;
+  static constexpr size_t kOffQidx = kOffHist + 1032 * 4;
+  static constexpr size_t kOffRed = kOffQidx + (size_t)kCH * 2;
+  static constexpr size_t kOffQueue = kOffRed + 64 * 4;
+  static constexpr size_t kSmemSlab = kOffQueue + (size_t)(kKnnQueue + kSlabT) * kQT * 2;
+  static constexpr size_t kSmem = kSmemSlab > SlabBase::kSmem ? kSmemSlab : SlabBase::kSmem;
+};
+
+// A query whose queue overflowed, served by the whole warp from the staged slab [w0, w1) (every one of its K nearest
+// lies there): each lane filters a strided share of the slab with the query's threshold and keeps the exact distances
+// of the survivors (a handful per warp) in registers; K rounds of a warp minimum then peel off the K smallest values
+// (duplicates one at a time).  More than kSlowSlots survivors in one lane (clouds of coincident points): K selection
+// passes over the slab in (value, position) order instead.  sqrt of ranks skip..K-1 to `row`.
+constexpr int kSlowSlots = 8;
+__device__ void slab_slow_query(const float4* __restrict__ tgt, int w0, int w1, int n, float qx, float qy, float qz,
+                                float ax2, float ay2, float az2, float thr, int K, int skip, float* __restrict__ row,
+                                int lane) {
+  const float kInf = __int_as_float(0x7f800000);
+  float c[kSlowSlots];
+#pragma unroll
+  for (int s = 0; s < kSlowSlots; s++) c[s] = kInf;
+  int nc = 0;
+  for (int p = (w0 >> 1) + lane; p < (w1 >> 1); p += 32) {
+    const float4 u = tgt[2 * p], v = tgt[2 * p + 1];
+    const float2 f = filter_pair(u, v, ax2, ay2, az2);
+    if (!(f.x > thr) && 2 * p < n) {
+      const float d = sqdist<GA_MODE_CPU_EXACT>(u.x, u.z, v.x, qx, qy, qz);
+#pragma unroll
+      for (int s = 0; s < kSlowSlots; s++) c[s] = s == nc ? d : c[s];
+      nc++;
+    }
+    if (!(f.y > thr) && 2 * p + 1 < n) {
+      const float d = sqdist<GA_MODE_CPU_EXACT>(u.y, u.w, v.y, qx, qy, qz);
+#pragma unroll
+      for (int s = 0; s < kSlowSlots; s++) c[s] = s == nc ? d : c[s];
+      nc++;
+    }
+  }
+  if (__any_sync(0xffffffffu, nc > kSlowSlots)) {
+    const float* tf = reinterpret_cast<const float*>(tgt);
+    const int hi = min(w1, n);
+    float pv = -kInf;
+    int pp = -1;
+    for (int s = 0; s < K; s++) {
+      float bv = kInf;
+      int bp = 0x7fffffff;
+      for (int i = w0 + lane; i < hi; i += 32) {
+        const float* pu = tf + 8 * (i >> 1) + (i & 1);
+        const float d = sqdist<GA_MODE_CPU_EXACT>(pu[0], pu[2], pu[4], qx, qy, qz);
+        const bool after = d > pv || (d == pv && i > pp);
+        if (after && (d < bv || (d == bv && i < bp))) {
+          bv = d;
+          bp = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (ov < bv || (ov == bv && op < bp)) {
+          bv = ov;
+          bp = op;
+        }
+      }
+      pv = bv;
+      pp = bp;
+      if (lane == 0 && s >= skip) row[s - skip] = __fsqrt_rn(pv);
+    }
+    return;
+  }
+  for (int s = 0; s < K; s++) {
+    float m = c[0];
+#pragma unroll
+    for (int e = 1; e < kSlowSlots; e++) m = fminf(m, c[e]);
+    float wm = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm = fminf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    const unsigned holders = __ballot_sync(0xffffffffu, m == wm);
+    if (lane == __ffs(holders) - 1) {  // one copy leaves
+      bool done = false;
+#pragma unroll
+      for (int e = 0; e < kSlowSlots; e++) {
+        const bool hit = !done && c[e] == wm;
+        c[e] = hit ? kInf : c[e];
+        done |= hit;
+      }
+    }
+    if (lane == 0 && s >= skip) row[s - skip] = __fsqrt_rn(wm);
+  }
+}
+
+#ifdef GA_SLAB_DEBUG
+__device__ unsigned long long g_slab_dbg[16];
+#define SLAB_DBG(i, v) atomicAdd(&g_slab_dbg[i], (unsigned long long)(v))
+#else
+#define SLAB_DBG(i, v)
+#endif
+__global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
+  constexpr int THREADS = SlabCfg::kThreads, QT = SlabCfg::kQT, KL = SlabCfg::kKL, T = kSlabT, CH = SlabCfg::kCH;
+  constexpr int PPT = CH / THREADS;  // points per thread in the sort
+  const float kInf = __int_as_float(0x7f800000);
+  extern __shared__ float4 smem_f4[];
+  unsigned char* smem_raw = reinterpret_cast<unsigned char*>(smem_f4);
+  float4* tgt = smem_f4;
+  int* hist = reinterpret_cast<int*>(smem_raw + SlabCfg::kOffHist);
+  unsigned short* qidx = reinterpret_cast<unsigned short*>(smem_raw + SlabCfg::kOffQidx);
+  float* red = reinterpret_cast<float*>(smem_raw + SlabCfg::kOffRed);
+  unsigned short* queue = reinterpret_cast<unsigned short*>(smem_raw + SlabCfg::kOffQueue);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int batch = blockIdx.x / a.qtiles;
+  const int qtile = blockIdx.x - batch * a.qtiles;
+  const int n = a.n, K = a.k;
+  const float* pts = a.xyz1 + (size_t)batch * n * 3;
+#ifdef GA_SLAB_DEBUG
+  long long tk0 = clock64();
+#define SLAB_CLK(i) do { if (tid == 0) { const long long t_ = clock64(); SLAB_DBG(i, t_ - tk0); tk0 = t_; } } while (0)
+#else
+#define SLAB_CLK(i)
+#endif
+
+  // ---- the cloud: coordinates to registers, x range, max |coordinate|, finiteness ----
+  float px[PPT], py[PPT], pz[PPT];
+  float xmin = kInf, xmax = -kInf, amax = 0.0f;
+  bool bad = false;
+#pragma unroll
+  for (int e = 0; e < PPT; e++) {
+    const int i = tid + e * THREADS;
+    const bool in = i < n;
+    px[e] = in ? __ldg(pts + (size_t)i * 3) : 0.0f;
+    py[e] = in ? __ldg(pts + (size_t)i * 3 + 1) : 0.0f;
+    pz[e] = in ? __ldg(pts + (size_t)i * 3 + 2) : 0.0f;
+    if (in) {
+      xmin = fminf(xmin, px[e]);
+      xmax = fmaxf(xmax, px[e]);
+      const float m = fmaxf(fmaxf(fabsf(px[e]), fabsf(py[e])), fabsf(pz[e]));
+      amax = fmaxf(amax, m);
+      // NaN, inf or a distance that could overflow (fmaxf drops NaNs: test every coordinate)
+      bad |= !(fabsf(px[e]) < 1.0e15f) || !(fabsf(py[e]) < 1.0e15f) || !(fabsf(pz[e]) < 1.0e15f);
+    }
+  }
+  for (int i = tid; i < 1032; i += THREADS) hist[i] = 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    red[warp] = xmin;
+    red[8 + warp] = xmax;
+    red[16 + warp] = amax;
+    red[24 + warp] = bad ? 1.0f : 0.0f;
+  }
+  __syncthreads();
+  float fbad = 0.0f;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; w++) {
+    xmin = fminf(xmin, red[w]);
+    xmax = fmaxf(xmax, red[8 + w]);
+    amax = fmaxf(amax, red[16 + w]);
+    fbad = fmaxf(fbad, red[24 + w]);
+  }
+  if (fbad != 0.0f || !(amax > 1.0e-15f)) {  // uniform over the CTAs of a cloud: every one of them read all of it
+    __syncthreads();
+    knn_body<SlabBase>(a);
+    return;
+  }
+
+  // ---- counting sort by x bin (monotonic in x), staged as pair-SoA in sorted order ----
+  const float ext = xmax - xmin;
+  const float inv = ext > 0.0f ? (float)kSlabBins / ext : 0.0f;
+  auto bin_of = [&](float x) {
+    const float t = (x - xmin) * inv;
+    int bi = t > 0.0f ? (t < (float)(kSlabBins - 1) ? (int)t : kSlabBins - 1) : 0;
+    return bi;
+  };
+  int rank[PPT], bins[PPT];
+#pragma unroll
+  for (int e = 0; e < PPT; e++) {
+    const int i = tid + e * THREADS;
+    bins[e] = bin_of(px[e]);
+    rank[e] = i < n ? atomicAdd(&hist[bins[e]], 1) : 0;
+  }
+  __syncthreads();
+  {  // exclusive scan of the 1024 counts: 4 bins per thread, warp scan, warp totals
+    const int c0 = hist[4 * tid], c1 = hist[4 * tid + 1], c2 = hist[4 * tid + 2], c3 = hist[4 * tid + 3];
+    const int tot = c0 + c1 + c2 + c3;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    int cmax = __reduce_max_sync(0xffffffffu, max(max(c0, c1), max(c2, c3)));
+    int* wsum = reinterpret_cast<int*>(red + 32);
+    if (lane == 31) wsum[warp] = inc;
+    if (lane == 0) wsum[8 + warp] = cmax;
+    __syncthreads();
+    int base = inc - tot;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+      if (w < warp) base += wsum[w];
+      cmax = max(cmax, wsum[8 + w]);
+    }
+    if (cmax > kSlabMaxBin) {  // many points with (nearly) the same x: no slab structure to use.  Uniform per cloud.
+      __syncthreads();
+      knn_body<SlabBase>(a);
+      return;
+    }
+    hist[4 * tid] = base;
+    hist[4 * tid + 1] = base + c0;
+    hist[4 * tid + 2] = base + c0 + c1;
+    hist[4 * tid + 3] = base + c0 + c1 + c2;
+    if (tid == THREADS - 1) hist[kSlabBins] = base + tot;  // = n
+  }
+  __syncthreads();
+  float* tf = reinterpret_cast<float*>(tgt);
+#pragma unroll
+  for (int e = 0; e < PPT; e++) {
+    const int i = tid + e * THREADS;
+    if (i < n) {
+      const int pos = hist[bins[e]] + rank[e];
+      float* pu = tf + 8 * (pos >> 1) + (pos & 1);
+      pu[0] = px[e];
+      pu[2] = py[e];
+      pu[4] = pz[e];
+      pu[6] = fmaf(pz[e], pz[e], fmaf(py[e], py[e], px[e] * px[e]));
+      qidx[pos] = (unsigned short)i;
+    }
+  }
+  const int npad = (n + T - 1) / T * T;
+  for (int pos = n + tid; pos < npad + 2 * kPipeU; pos += THREADS) {  // padding: far away, never a candidate
+    float* pu = tf + 8 * (pos >> 1) + (pos & 1);
+    pu[0] = 0.0f;
+    pu[2] = 0.0f;
+    pu[4] = 0.0f;
+    pu[6] = kInf;
+  }
+  __syncthreads();
+  // The atomics above order the points of a bin arbitrarily, differently in every CTA of the cloud; the CTAs split
+  // the queries by sorted POSITION, so the order has to be the same everywhere: points of a bin by original index
+  // (insertion sort of a handful of entries; a thread owns four bins, the words of an entry are its own).
+  for (int bb = 0; bb < 4; bb++) {
+    const int s0 = hist[4 * tid + bb], s1 = hist[4 * tid + bb + 1];
+    for (int i = s0 + 1; i < s1; i++) {
+      const unsigned short qi = qidx[i];
+      const float* pi = tf + 8 * (i >> 1) + (i & 1);
+      const float ex = pi[0], ey = pi[2], ez = pi[4], en = pi[6];
+      int j = i - 1;
+      while (j >= s0 && qidx[j] > qi) {
+        const float* pj = tf + 8 * (j >> 1) + (j & 1);
+        float* pd = tf + 8 * ((j + 1) >> 1) + ((j + 1) & 1);
+        pd[0] = pj[0];
+        pd[2] = pj[2];
+        pd[4] = pj[4];
+        pd[6] = pj[6];
+        qidx[j + 1] = qidx[j];
+        j--;
+      }
+      float* pd = tf + 8 * ((j + 1) >> 1) + ((j + 1) & 1);
+      pd[0] = ex;
+      pd[2] = ey;
+      pd[4] = ez;
+      pd[6] = en;
+      qidx[j + 1] = qi;
+    }
+  }
+  __syncthreads();
+
+  // ---- the warp's 64 queries: sorted positions base .. base + 63 (no barrier below) ----
+  const int base = qtile * QT + warp * 64;
+  if (base >= n) return;
+  {
+  float qx[2], qy[2], qz[2], qabs[2], ax2[2], ay2[2], az2[2], qn[2];
+  bool valid[2];
+  float xa = kInf, xb = -kInf;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int pos = base + 32 * j + lane;
+    valid[j] = pos < n;
+    const int ps = valid[j] ? pos : base;
+    const float* pu = tf + 8 * (ps >> 1) + (ps & 1);
+    qx[j] = pu[0];
+    qy[j] = pu[2];
+    qz[j] = pu[4];
+    qn[j] = pu[6];
+    qabs[j] = fmaxf(fmaxf(fabsf(qx[j]), fabsf(qy[j])), fabsf(qz[j]));
+    ax2[j] = -2.0f * qx[j];
+    ay2[j] = -2.0f * qy[j];
+    az2[j] = -2.0f * qz[j];
+    xa = fminf(xa, qx[j]);
+    xb = fmaxf(xb, qx[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xa = fminf(xa, __shfl_xor_sync(0xffffffffu, xa, o));
+    xb = fmaxf(xb, __shfl_xor_sync(0xffffffffu, xb, o));
+  }
+
+  // ---- A0: K-th smallest tile minimum around the warp's own positions ----
+  float tau[2];
+  {
+    const int t0 = max(0, base - kSlabSeed) & ~(T - 1);
+    const int t1 = min(npad, (base + 64 + kSlabSeed + T - 1) & ~(T - 1));
+    float S[2][KL];
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int s = 0; s < KL; s++) S[j][s] = kInf;
+    filter_scan<2, T>(tgt + t0, (t1 - t0) / T, ax2, ay2, az2, [&](int, const float(&tm)[2]) {
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        float v = tm[j];
+#pragma unroll
+        for (int s = 0; s < KL; s++) {  // sorted insert by compare-exchange chain
+          const float lo = fminf(S[j][s], v);
+          v = fmaxf(S[j][s], v);
+          S[j][s] = lo;
+        }
+      }
+    });
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      float tk = kInf;
+#pragma unroll
+      for (int s = 0; s < KL; s++)
+        if (s == K - 1) tk = S[j][s];
+      tau[j] = tk;
+    }
+  }
+
+  SLAB_CLK(9);
+  // ---- the slab that can hold a K-th neighbour of any of the warp's queries ----
+  int w0 = 0, w1 = npad;
+  {
+    float U = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const float s = (qabs[j] + amax) * 1.0001f;
+      const float uj = fmaf(fmaxf(tau[j] + qn[j], 0.0f), 1.0009765625f, s * s * 7.62939453125e-06f /* 2^-17 */);
+      U = fmaxf(U, valid[j] ? uj : 0.0f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) U = fmaxf(U, __shfl_xor_sync(0xffffffffu, U, o));
+    const float r = __fmul_ru(__fsqrt_ru(U), 1.000001f);
+    if (__fmul_rn(r, r) > U && r < kInf) {  // otherwise (tau = +inf: fewer than K tiles around) keep the whole cloud
+      const float lo = __fsub_rd(xa, r), hi = __fadd_ru(xb, r);
+      const int b0 = bin_of(lo), b1 = bin_of(hi);
+      w0 = hist[b0] & ~(T - 1);
+      w1 = min(npad, (hist[b1 + 1] + T - 1) & ~(T - 1));
+    }
+  }
+
+  // ---- B1: candidates of the slab into the queues ----
+  float thr[2];
+  int cnts[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    thr[j] = valid[j] ? tau[j] + filter_window(qabs[j], amax) : -kInf;
+    cnts[j] = 0;
+  }
+  filter_collect<2, T>(tgt + w0, (w1 - w0) / T, ax2, ay2, az2, thr, cnts, queue + tid, QT, THREADS, kKnnQueue);
+
+  SLAB_CLK(10);
+#ifdef GA_SLAB_DEBUG
+  if (lane == 0) {
+    SLAB_DBG(0, 1);
+    SLAB_DBG(1, w1 - w0);
+    SLAB_DBG(2, w1 - w0 == npad);
+  }
+  for (int j = 0; j < 2; j++)
+    if (valid[j]) {
+      SLAB_DBG(3, 1);
+      SLAB_DBG(4, cnts[j]);
+      SLAB_DBG(5, cnts[j] > kKnnQueue);
+      SLAB_DBG(6, !(tau[j] < 1e30f));
+    }
+#endif
+  // ---- B2: exact list of the K smallest values ----
+  const int kout = K - a.skip;
+  bool over[2];
+  {
+    // values only: a branch-free compare-exchange chain keeps the KL smallest (equal values need no order); the
+    // lane's two queries are drained in one loop, two independent chains in flight
+    float TLv[2][KL];
+    int take[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      over[j] = valid[j] && cnts[j] > kKnnQueue;
+      take[j] = (valid[j] && !over[j]) ? cnts[j] : 0;
+#pragma unroll
+      for (int s = 0; s < KL; s++) TLv[j][s] = kInf;
+    }
+    const int cmaxq = max(take[0], take[1]);
+    for (int c = 0; c < cmaxq; c++) {
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const bool on = c < take[j];
+        const int gl = on ? w0 + queue[c * QT + j * THREADS + tid] : 0;
+        const float* pu = tf + 8 * (gl >> 1) + (gl & 1);
+        float v = sqdist<GA_MODE_CPU_EXACT>(pu[0], pu[2], pu[4], qx[j], qy[j], qz[j]);
+        v = (on && gl < n) ? v : kInf;  // padding is only reachable with a non-finite threshold
+#pragma unroll
+        for (int s = 0; s < KL; s++) {
+          const float lo = fminf(TLv[j][s], v);
+          v = fmaxf(TLv[j][s], v);
+          TLv[j][s] = lo;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      if (!valid[j] || over[j]) continue;
+      bool shortlist = false;
+#pragma unroll
+      for (int s = 0; s < KL; s++)
+        if (s == K - 1) shortlist = !(TLv[j][s] < kInf);
+      if (shortlist) {  // cannot happen for finite data (K targets with f <= tau lie in the slab); be safe
+        SLAB_DBG(7, 1);
+        over[j] = true;
+        continue;
+      }
+      float* vo = a.val + ((size_t)batch * n + qidx[base + 32 * j + lane]) * kout;
+#pragma unroll
+      for (int s = 0; s < KL; s++)
+        if (s >= a.skip && s < K) vo[s - a.skip] = a.do_sqrt ? __fsqrt_rn(TLv[j][s]) : TLv[j][s];
+    }
+  }
+  SLAB_CLK(11);
+  // ---- overflowed queues (dense clusters): the whole warp serves the query ----
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    unsigned pending = __ballot_sync(0xffffffffu, over[j]);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const float bx = __shfl_sync(0xffffffffu, qx[j], src), by = __shfl_sync(0xffffffffu, qy[j], src),
+                  bz = __shfl_sync(0xffffffffu, qz[j], src);
+      // the threshold filter_collect started with (it overwrites thr[] of an overflowed query)
+      const float bthr = __shfl_sync(0xffffffffu, tau[j] + filter_window(qabs[j], amax), src);
+      slab_slow_query(tgt, w0, w1, n, bx, by, bz, -2.0f * bx, -2.0f * by, -2.0f * bz, bthr, K, a.skip,
+                      a.val + ((size_t)batch * n + qidx[base + 32 * j + src]) * kout, lane);
+    }
+  }
+  SLAB_CLK(12);
+  }
+}
+
+#ifdef GA_SLAB_DEBUG
+extern "C" int ga_debug_slab_stats(unsigned long long* out8) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_slab_dbg, 128);
+  unsigned long long z[16] = {};
+  cudaMemcpyToSymbol(g_slab_dbg, z, 128);
+  return 0;
+}
+#endif
+int g_knn_slab = 1;  // tuning hook (key 28): 0 = ga_knn_dists never takes knn_slab_kernel, 1 = large batches, 2 = always
+
+static int launch_knn_slab(const KnnArgs& a0, cudaStream_t st) {
+  KnnArgs a = a0;
+  a.qtiles = (a.m + SlabCfg::kQT - 1) / SlabCfg::kQT;
+  const long long ctas = (long long)a.b * a.qtiles;
+  if (ctas > 0x7fffffffLL) {
+    set_error("ga_knn: problem too large for one launch");
+    return GA_ERR_UNSUPPORTED;
+  }
+  GA_CUDA_TRY(cudaFuncSetAttribute(knn_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SlabCfg::kSmem));
+  knn_slab_kernel<<<(unsigned)ctas, SlabCfg::kThreads, SlabCfg::kSmem, st>>>(a);
+  GA_LAUNCH_CHECK("knn_slab_kernel");
+  return GA_OK;
+}
+
+template <class Cfg>
 static int launch_knn(const KnnArgs& a0, cudaStream_t st) {
   KnnArgs a = a0;
   a.qtiles = (a.m + Cfg::kQT - 1) / Cfg::kQT;
@@ -883,6 +1393,15 @@ static int knn_dispatch(const KnnArgs& a, cudaStream_t st) {
     if (a.n <= 2048) {  // single chunk: lists live only while a query slot is drained
       if (kl <= 12) {
         int variant = g_knn_variant;
+        // values only, self-kNN, sqrt epilogue (ga_knn_dists): the slab-pruned kernel; knn_point proper needs the
+        // reference's tie order and keeps the full scans
+        // (from two full waves of its 512-query CTAs on: one CTA is a long chain of dependent phases, 240 us where
+        // knn_kernel's takes 186, and only pays when other CTAs fill the gaps -- B=50 0.24 vs 0.19 ms, B=500 0.79 vs
+        // 1.14 ms; key 28 = 2 takes it at any size)
+        if (variant == 0 && g_knn_slab && a.idx == nullptr && a.xyz1 == a.xyz2 && a.n == a.m && a.n >= 512 &&
+            a.do_sqrt && a.skip <= 1 && a.k >= 2 &&
+            (g_knn_slab >= 2 || (long long)a.b * ((a.m + 511) / 512) >= 4LL * sm_count()))
+          return launch_knn_slab(a, st);
         // tensor-core scans (opt-in, variant 6; data sets of at least 4 MMA blocks): bit-exact, but at config 5 it
         // takes 2.18 ms against 1.11 ms for the fp32-filter kernel -- 40 K warp instructions per 64 queries (two MMA
         // scans 8 K, tile walk 9 K, drain 10 K, setup) at 35 % issue utilisation with one 16-warp CTA per SM

@@ -209,3 +209,100 @@ def test_knn_mma_equals_fp32_kernel_at_full_size(ga, knn_mma):
     v3, i3 = ga.knn_point(11, pc, pc)
     lib.ga_set_tuning(1, 6)
     assert torch.equal(v6, v3) and torch.equal(i6, i3)
+
+
+# ---- knn_slab_kernel: ga_knn_dists with the scans pruned to an x-slab (values only) -----------------------------
+def _slab_clouds():
+    rng = np.random.default_rng(11)
+    out = {}
+    out["uniform_2048"] = cloud(21, (6, 2048, 3))
+    out["ragged_2047"] = cloud(22, (3, 2047, 3))
+    out["n1000"] = cloud(23, (3, 1000, 3))
+    out["n512"] = cloud(24, (2, 512, 3))
+    out["n1500_offset"] = (cloud(25, (2, 1500, 3)) + np.float32(7.25)).astype(np.float32)
+    blobs = (rng.standard_normal((3, 2048, 3)) * 0.01).astype(np.float32)
+    blobs += rng.integers(0, 4, (3, 2048, 1)).astype(np.float32) * np.float32(0.5)      # four tight clusters
+    out["clusters"] = blobs
+    dup = cloud(26, (2, 2048, 3))
+    dup[:, 1024:] = dup[:, :1024]                                                          # every point twice
+    out["duplicates"] = dup
+    grid = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(8), indexing="ij"), -1).reshape(1, 2048, 3)
+    out["lattice_ties"] = (grid * np.float32(0.125)).astype(np.float32)                  # exact ties everywhere
+    plane = cloud(27, (2, 2048, 3))
+    plane[..., 0] = np.float32(0.3)                                                        # all x equal: one bin
+    out["plane_x_const"] = plane
+    line = np.zeros((1, 2048, 3), np.float32)
+    line[0, :, 0] = np.linspace(-1, 1, 2048, dtype=np.float32)                             # a line along x
+    out["line"] = line
+    same = np.full((1, 600, 3), 0.25, np.float32)                                          # one point 600 times
+    out["all_equal"] = same
+    tiny = (cloud(28, (2, 2048, 3)) * np.float32(1e-12)).astype(np.float32)
+    out["tiny_coordinates"] = tiny
+    huge = (cloud(29, (2, 2048, 3)) * np.float32(1e12)).astype(np.float32)
+    out["huge_coordinates"] = huge
+    surf = cloud(30, (3, 2048, 3))
+    surf /= np.linalg.norm(surf, axis=-1, keepdims=True).astype(np.float32)              # points on a sphere
+    out["sphere_surface"] = surf.astype(np.float32)
+    return out
+
+
+@pytest.mark.parametrize("k", [1, 4, 10])
+@pytest.mark.parametrize("name", list(_slab_clouds().keys()))
+def test_knn_slab_equals_full_scan_kernel(ga, name, k):
+    """The slab-pruned kernel against knn_kernel (key 28 = 0): the same bits, whatever the cloud looks like."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    pc = _slab_clouds()[name]
+    lib.ga_set_tuning(28, 2)
+    got = ga.knn_dists(t(pc), k)
+    assert _lib.load().ga_last_kernel().decode() == "knn_slab_kernel"
+    lib.ga_set_tuning(28, 0)
+    try:
+        want = ga.knn_dists(t(pc), k)
+        assert _lib.load().ga_last_kernel().decode() == "knn_kernel"
+    finally:
+        lib.ga_set_tuning(28, 1)
+    assert bits_equal(got.cpu().numpy(), want.cpu().numpy()), (name, k, int((got != want).sum()))
+
+
+def test_knn_slab_equals_oracle_and_handles_non_finite(ga, oracle):
+    from geometric_adv_b200 import _lib
+    _lib.load().ga_set_tuning(28, 2)
+    pc = cloud(31, (5, 2048, 3))
+    got = ga.knn_dists(t(pc), 10).cpu().numpy()
+    assert _lib.load().ga_last_kernel().decode() == "knn_slab_kernel"
+    assert bits_equal(got, oracle.knn_dists(pc, 10))
+    assert bits_equal(got[:1], oracle.knn_dists_numpy(pc[:1], 10))
+    # a cloud with a NaN / inf point is handed to the full-scan body inside the same launch; its neighbours in the
+    # batch are not affected
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    bad = pc.copy()
+    bad[1, 77, 1] = np.nan
+    bad[3, 5, 0] = np.inf
+    lib.ga_set_tuning(28, 2)
+    got = ga.knn_dists(t(bad), 10).cpu().numpy()
+    lib.ga_set_tuning(28, 0)
+    try:
+        want = ga.knn_dists(t(bad), 10).cpu().numpy()
+    finally:
+        lib.ga_set_tuning(28, 1)
+    assert bits_equal(got, want)
+    assert bits_equal(got[[0, 2, 4]], oracle.knn_dists(pc[[0, 2, 4]], 10))
+
+
+def test_knn_slab_full_size_config5(ga, oracle):
+    """B=500 x 2048, k=10: bitwise equal to the full-scan kernel, 32 clouds against the oracle."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    pc = cloud(4, (500, 2048, 3))
+    got = ga.knn_dists(t(pc), 10)
+    assert _lib.load().ga_last_kernel().decode() == "knn_slab_kernel"
+    lib.ga_set_tuning(28, 0)
+    try:
+        want = ga.knn_dists(t(pc), 10)
+    finally:
+        lib.ga_set_tuning(28, 1)
+    assert torch.equal(got, want)
+    sel = np.arange(0, 500, 16)
+    assert bits_equal(got[sel].cpu().numpy(), oracle.knn_dists(pc[sel], 10))
