@@ -313,6 +313,32 @@ __device__ __forceinline__ void knn_body(const KnnArgs& a) {
         overflow[j] = true;
         continue;
       }
+      if (!need_idx && !MULTI) {
+        // values only (ga_knn_dists): equal distances need no order, so a branch-free compare-exchange chain
+        // replaces the index-ordered insert (a third of knn_slab_kernel's instructions before it did the same)
+        float V[KL];
+#pragma unroll
+        for (int s = 0; s < KL; s++) V[s] = kInf;
+        for (int c = 0; c < cnt; c++) {
+          const int gl = myq[c * QT];
+          const float* pu = reinterpret_cast<const float*>(tgt + 2 * (gl >> 1));
+          const int h = gl & 1;
+          float v = sqdist<GA_MODE_CPU_EXACT>(pu[h], pu[2 + h], pu[4 + h], qx[j], qy[j], qz[j]);
+          v = (v == v && c0 + gl < n) ? v : kInf;  // NaN is never selected beyond position k; padding
+#pragma unroll
+          for (int s = 0; s < KL; s++) {
+            const float lo = fminf(V[s], v);
+            v = fmaxf(V[s], v);
+            V[s] = lo;
+          }
+        }
+        const int qi = qtile * QT + j * THREADS + tid;
+        float* vo = a.val + ((size_t)batch * a.m + qi) * kout;
+#pragma unroll
+        for (int s = 0; s < KL; s++)
+          if (s >= a.skip && s < k) vo[s - a.skip] = a.do_sqrt ? __fsqrt_rn(V[s]) : V[s];
+        continue;
+      }
       // B2: drain the queue into the exact sorted list (all lanes step through their own
       // queue together; the insert is order-independent)
       float TLv[KL];

@@ -60,6 +60,11 @@ def all_gather_rows(block, total_rows, group=None):
         return out
     pad = torch.zeros((maxrows,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
     pad[: block.shape[0]] = block
+    if block.is_cuda:  # unequal blocks: ONE all-gather of blocks padded to the largest, then the pads drop out
+        gathered = torch.empty((world * maxrows,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(gathered, pad, group=group)
+        parts = gathered.view((world, maxrows) + tuple(block.shape[1:]))
+        return torch.cat([parts[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
     return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
