@@ -913,19 +913,20 @@ __global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
 // cloud.  A cloud with a non-finite or huge coordinate, or fewer than 512 points, is handed to knn_body unchanged
 // (NaN distances take part in the reference's selection sort in a way only its replay reproduces).
 constexpr int kSlabBins = 1024;
-constexpr int kSlabSeed = 160;
+constexpr int kSlabSeed = 224;   // targets on either side of a warp's own positions in the first scan
+constexpr int kSlabQueue = 40;   // candidate slots per query
 constexpr int kSlabT = 16;
 constexpr int kSlabMaxBin = 32;  // fullest bin the slab path takes (its points get an insertion sort by index)
 
 using SlabBase = KnnCfg<256, 2, 32, 2048, 12, false>;
 struct SlabCfg {
   static constexpr int kThreads = 256, kQ = 2, kQT = 512, kCH = 2048, kKL = 12;
-  // tgt (+ pipeline pad) | hist/starts int[1026] | qidx u16[2048] | red[64] | queue u16[(32 + 16)][512]
+  // tgt (+ pipeline pad) | hist/starts int[1026] | qidx u16[2048] | red[64] | queue u16[(40 + 16)][512]
   static constexpr size_t kOffHist = (size_t)kCH * 16 + (size_t)kPipeU * 32;
   static constexpr size_t kOffQidx = kOffHist + 1032 * 4;
   static constexpr size_t kOffRed = kOffQidx + (size_t)kCH * 2;
   static constexpr size_t kOffQueue = kOffRed + 64 * 4;
-  static constexpr size_t kSmemSlab = kOffQueue + (size_t)(kKnnQueue + kSlabT) * kQT * 2;
+  static constexpr size_t kSmemSlab = kOffQueue + (size_t)(kSlabQueue + kSlabT) * kQT * 2;
   static constexpr size_t kSmem = kSmemSlab > SlabBase::kSmem ? kSmemSlab : SlabBase::kSmem;
 };
 
@@ -991,6 +992,7 @@ __device__ void slab_slow_query(const float4* __restrict__ tgt, int w0, int w1, 
     }
     return;
   }
+  float mine = kInf;  // lane s keeps the s-th smallest (K <= 32)
   for (int s = 0; s < K; s++) {
     float m = c[0];
 #pragma unroll
@@ -1008,8 +1010,9 @@ __device__ void slab_slow_query(const float4* __restrict__ tgt, int w0, int w1, 
         done |= hit;
       }
     }
-    if (lane == 0 && s >= skip) row[s - skip] = __fsqrt_rn(wm);
+    if (lane == s) mine = wm;
   }
+  if (lane >= skip && lane < K) row[lane - skip] = __fsqrt_rn(mine);  // one store for the row
 }
 
 #ifdef GA_SLAB_DEBUG
@@ -1195,6 +1198,11 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
   // ---- the warp's 64 queries: sorted positions base .. base + 63 (no barrier below) ----
   const int base = qtile * QT + warp * 64;
   if (base >= n) return;
+#ifdef GA_SLAB_DEBUG
+  const long long tw0 = clock64();
+  long long tslow0 = 0;
+  int nslow = 0;
+#endif
   {
   float qx[2], qy[2], qz[2], qabs[2], ax2[2], ay2[2], az2[2], qn[2];
   bool valid[2];
@@ -1225,8 +1233,12 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
   // ---- A0: K-th smallest tile minimum around the warp's own positions ----
   float tau[2];
   {
-    const int t0 = max(0, base - kSlabSeed) & ~(T - 1);
-    const int t1 = min(npad, (base + 64 + kSlabSeed + T - 1) & ~(T - 1));
+    // the same number of targets at the ends of the cloud, where one side is cut off (a half ball reaches further:
+    // without this the end warps' tau is loose and every one of their queues overflows)
+    int t0 = max(0, base - kSlabSeed) & ~(T - 1);
+    int t1 = min(npad, (base + 64 + kSlabSeed + T - 1) & ~(T - 1));
+    if (t0 == 0) t1 = min(npad, max(t1, 64 + 2 * kSlabSeed));
+    if (t1 == npad) t0 = max(0, min(t0, npad - (64 + 2 * kSlabSeed)));
     float S[2][KL];
 #pragma unroll
     for (int j = 0; j < 2; j++)
@@ -1284,7 +1296,7 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
     thr[j] = valid[j] ? tau[j] + filter_window(qabs[j], amax) : -kInf;
     cnts[j] = 0;
   }
-  filter_collect<2, T>(tgt + w0, (w1 - w0) / T, ax2, ay2, az2, thr, cnts, queue + tid, QT, THREADS, kKnnQueue);
+  filter_collect<2, T>(tgt + w0, (w1 - w0) / T, ax2, ay2, az2, thr, cnts, queue + tid, QT, THREADS, kSlabQueue);
 
   SLAB_CLK(10);
 #ifdef GA_SLAB_DEBUG
@@ -1293,13 +1305,6 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
     SLAB_DBG(1, w1 - w0);
     SLAB_DBG(2, w1 - w0 == npad);
   }
-  for (int j = 0; j < 2; j++)
-    if (valid[j]) {
-      SLAB_DBG(3, 1);
-      SLAB_DBG(4, cnts[j]);
-      SLAB_DBG(5, cnts[j] > kKnnQueue);
-      SLAB_DBG(6, !(tau[j] < 1e30f));
-    }
 #endif
   // ---- B2: exact list of the K smallest values ----
   const int kout = K - a.skip;
@@ -1311,7 +1316,7 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
     int take[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-      over[j] = valid[j] && cnts[j] > kKnnQueue;
+      over[j] = valid[j] && cnts[j] > kSlabQueue;
       take[j] = (valid[j] && !over[j]) ? cnts[j] : 0;
 #pragma unroll
       for (int s = 0; s < KL; s++) TLv[j][s] = kInf;
@@ -1352,6 +1357,9 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
     }
   }
   SLAB_CLK(11);
+#ifdef GA_SLAB_DEBUG
+  tslow0 = clock64();
+#endif
   // ---- overflowed queues (dense clusters): the whole warp serves the query ----
 #pragma unroll
   for (int j = 0; j < 2; j++) {
@@ -1359,6 +1367,9 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
     while (pending) {
       const int src = __ffs(pending) - 1;
       pending &= pending - 1;
+#ifdef GA_SLAB_DEBUG
+      nslow++;
+#endif
       const float bx = __shfl_sync(0xffffffffu, qx[j], src), by = __shfl_sync(0xffffffffu, qy[j], src),
                   bz = __shfl_sync(0xffffffffu, qz[j], src);
       // the threshold filter_collect started with (it overwrites thr[] of an overflowed query)
@@ -1369,6 +1380,15 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
   }
   SLAB_CLK(12);
   }
+#ifdef GA_SLAB_DEBUG
+  if (lane == 0) {
+    const long long t1 = clock64();
+    atomicAdd(&g_slab_dbg[13], (unsigned long long)(t1 - tw0));
+    atomicMax(&g_slab_dbg[14], (unsigned long long)(t1 - tw0));
+    atomicMax(&g_slab_dbg[15], (unsigned long long)(t1 - tslow0));
+    atomicMax(&g_slab_dbg[6], (unsigned long long)nslow);
+  }
+#endif
 }
 
 #ifdef GA_SLAB_DEBUG
@@ -1380,7 +1400,7 @@ extern "C" int ga_debug_slab_stats(unsigned long long* out8) {
   return 0;
 }
 #endif
-int g_knn_slab = 1;  // tuning hook (key 28): 0 = ga_knn_dists never takes knn_slab_kernel, 1 = large batches, 2 = always
+int g_knn_slab = 1;  // tuning hook (key 28): 0 = ga_knn_dists never takes knn_slab_kernel, 1 = from half a wave of CTAs, 2 = always
 
 static int launch_knn_slab(const KnnArgs& a0, cudaStream_t st) {
   KnnArgs a = a0;
@@ -1421,12 +1441,11 @@ static int knn_dispatch(const KnnArgs& a, cudaStream_t st) {
         int variant = g_knn_variant;
         // values only, self-kNN, sqrt epilogue (ga_knn_dists): the slab-pruned kernel; knn_point proper needs the
         // reference's tie order and keeps the full scans
-        // (from two full waves of its 512-query CTAs on: one CTA is a long chain of dependent phases, 240 us where
-        // knn_kernel's takes 186, and only pays when other CTAs fill the gaps -- B=50 0.24 vs 0.19 ms, B=500 0.79 vs
-        // 1.14 ms; key 28 = 2 takes it at any size)
+        // (measured, 2048-point clouds, ms slab / full scans: B=500 0.48 / 0.97, 250 0.26 / 0.50, 125 0.17 / 0.28,
+        // 50 0.105 / 0.142; from half a wave of its 512-query CTAs on; key 28 = 2 takes it at any size)
         if (variant == 0 && g_knn_slab && a.idx == nullptr && a.xyz1 == a.xyz2 && a.n == a.m && a.n >= 512 &&
             a.do_sqrt && a.skip <= 1 && a.k >= 2 &&
-            (g_knn_slab >= 2 || (long long)a.b * ((a.m + 511) / 512) >= 4LL * sm_count()))
+            (g_knn_slab >= 2 || (long long)a.b * ((a.m + 511) / 512) >= sm_count() / 2))
           return launch_knn_slab(a, st);
         // tensor-core scans (opt-in, variant 6; data sets of at least 4 MMA blocks): bit-exact, but at config 5 it
         // takes 2.18 ms against 1.11 ms for the fp32-filter kernel -- 40 K warp instructions per 64 queries (two MMA
