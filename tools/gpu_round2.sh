@@ -14,7 +14,7 @@ cat gpurun_out/bench_ref_${TAG}.json
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 216 -c 300 --csv \
   --log-file gpurun_out/launches_bench_${TAG}.csv python bench.py --steps 20 --warmup 3 --no-attack --no-legs > gpurun_out/launches_bench.log 2>&1
 for what in fwd bwd knn; do
-  case $what in fwd) RX=nn_fwd;; bwd) RX=nn_bwd;; knn) RX=knn_kernel;; esac
+  case $what in fwd) RX=nn_fwd;; bwd) RX=nn_bwd;; knn) RX=knn_;; esac
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$RX -s 2 -c 1 -f \
     -o gpurun_out/${TAG}_${what} python tools/prof.py $what 50 > gpurun_out/ncu_${what}.log 2>&1
 done
