@@ -38,6 +38,22 @@ def _world(group):
     return 1, 0
 
 
+_BYTEWISE = (torch.int16, torch.bool, torch.uint16)  # element types NCCL's all-gather does not take
+
+
+def _rows_as_bytes(block):
+    """(rows, ...) of any element type -> (rows, bytes per row) uint8, no copy for contiguous input."""
+    rowbytes = block.element_size()
+    for d in block.shape[1:]:
+        rowbytes *= int(d)
+    return block.contiguous().view(torch.uint8).reshape(block.shape[0], rowbytes)
+
+
+def _rows_from_bytes(flat, dtype, tail):
+    """Inverse of _rows_as_bytes for a (rows, bytes per row) uint8 tensor."""
+    return flat.contiguous().view(dtype).reshape((flat.shape[0],) + tuple(tail))
+
+
 def all_gather_rows(block, total_rows, group=None):
     """All-gather row blocks produced with shard_range into the full (total_rows, ...) tensor."""
     world, rank = _world(group)
@@ -45,13 +61,9 @@ def all_gather_rows(block, total_rows, group=None):
         return block
     # NCCL moves bytes of a handful of element types; int16 (the nn_idx stage file's type) and bool are not among
     # them: gather such blocks as raw bytes and view the result back
-    if block.is_cuda and block.dtype in (torch.int16, torch.bool, torch.uint16):
-        rowbytes = block.element_size()
-        for d in block.shape[1:]:
-            rowbytes *= int(d)
-        flat = block.contiguous().view(torch.uint8).reshape(block.shape[0], rowbytes)
-        out = all_gather_rows(flat, total_rows, group)
-        return out.view(block.dtype).reshape((total_rows,) + tuple(block.shape[1:]))
+    if block.is_cuda and block.dtype in _BYTEWISE:
+        out = all_gather_rows(_rows_as_bytes(block), total_rows, group)
+        return _rows_from_bytes(out, block.dtype, tuple(block.shape[1:]))
     sizes = [shard_range(total_rows, world, r) for r in range(world)]
     maxrows = max(hi - lo for lo, hi in sizes)
     if total_rows % world == 0 and block.is_cuda:  # equal blocks: one NCCL all-gather straight into the result

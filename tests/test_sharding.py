@@ -144,3 +144,19 @@ def test_sel_idx_rand_file(tmp_path):
         k = min(n, 100)
         assert np.array_equal(sel[i, :k], perm[:k]) and np.all(sel[i, k:] == -1)
         assert len(set(sel[i, :k].tolist())) == k
+
+
+def test_rows_travel_as_bytes_for_types_nccl_refuses():
+    """all_gather_rows moves int16 / bool blocks as bytes on CUDA (NCCL has no such element type: the all-pairs leg
+    failed under torchrun before); the view round-trips bit for bit, for empty and multi-dimensional blocks too."""
+    import torch
+    from geometric_adv_b200 import sharding
+    g = torch.Generator().manual_seed(0)
+    for shape in [(7, 5), (0, 5), (3,), (4, 2, 3)]:
+        a = torch.randint(-32768, 32767, shape, generator=g, dtype=torch.int32).to(torch.int16)
+        flat = sharding._rows_as_bytes(a)
+        assert flat.dtype == torch.uint8 and flat.shape[0] == shape[0] and flat.dim() == 2
+        assert torch.equal(sharding._rows_from_bytes(flat, torch.int16, shape[1:]), a)
+    b = torch.rand(6, 9, generator=g) > 0.5
+    assert torch.equal(sharding._rows_from_bytes(sharding._rows_as_bytes(b), torch.bool, (9,)), b)
+    assert torch.int16 in sharding._BYTEWISE
