@@ -25,6 +25,7 @@ extern int g_host_graph_epoch;   // host_api.cu
 extern int g_host_graph_mirror;  // host_api.cu
 extern int g_host_stream;        // host_api.cu
 extern int g_host_pull;          // host_api.cu
+extern int g_host_pull_mute;     // host_api.cu
 extern int g_knn_slab;           // grouping.cu
 extern int g_umma_grid;          // nn_distance_fwd_umma.cu
 extern int g_bwd_stage;          // nn_distance_bwd.cu
@@ -291,6 +292,11 @@ int ga_set_tuning(int key, int value) {
   if (key == 25) {
     ga::g_frame = value;
     ga::g_frame_clear.store(1, std::memory_order_relaxed);
+    return GA_OK;
+  }
+  if (key == 29) {
+    ga::g_host_pull_mute = value;
+    ga::g_host_graph_epoch++;
     return GA_OK;
   }
   if (key == 28) {

@@ -152,6 +152,7 @@ struct PullArgs {
   int4* dst2;
   int* ready;
   int b, v1, v2;
+  int mute;  // test hook (key 29): the flag of the last batch element is never raised
 };
 
 __global__ void __launch_bounds__(256) ingest_stream_kernel(const PullArgs a) {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) ingest_stream_kernel(const PullArgs a) {
       }
     }
     __syncthreads();  // every thread's stores are issued ...
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !(a.mute && e == a.b - 1)) {
       __threadfence();  // ... and ordered before the flag (cumulative over the barrier)
       asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ready + e), "r"(1) : "memory");
     }
@@ -216,6 +217,7 @@ static bool device_can_touch(const void* p) {
 int g_host_graph = 0;         // tuning hook (key 10): 0 auto, 1 never replay, 2 capture on first sight
 int g_host_graph_chunks = 0;  // tuning hook (key 11): chunks of the captured pipeline (0 = auto)
 int g_host_graph_epoch = 0;   // bumped by ga_set_tuning(10 | 11 | 17): cached graphs of older epochs are dropped
+int g_host_pull_mute = 0;     // test hook (key 29): 1 = the ingest kernel withholds one arrival flag (exercises the give-up path)
 int g_host_pull = 0;          // tuning hook (key 27): clouds pulled by the SMs behind arrival flags: 0 auto, -1 off, n = ingest CTAs
 int g_host_stream = 0;        // tuning hook (key 26): streamed ingest of the replayed step: 0 off, n = arrival groups
 int g_host_graph_mirror = 0;  // tuning hook (key 17): 0 auto, 1 = always copy dist/idx, 2 = always let the forward
@@ -420,6 +422,7 @@ static int issue_pipeline_pulled(const FwdBwdBufs& f, int b, int n, int m, int m
   pa.b = b;
   pa.v1 = n * 12 / 16;
   pa.v2 = m * 12 / 16;
+  pa.mute = g_host_pull_mute;
   ingest_stream_kernel<<<ctas < b ? ctas : b, 256, 0, sk>>>(pa);
   GA_LAUNCH_CHECK("ingest_stream_kernel");
 

@@ -232,6 +232,9 @@ int ga_probe_fp32_peak(int iters, float* tflops, float* ms, ga_stream_t stream);
  *      HMMA grid kernel, n and m are multiples of 32 and the clouds are device-readable pinned memory; -1 = off;
  *      n > 0 = that many ingest CTAs): a few CTAs load the clouds over PCIe, one arrival flag per batch element, the
  *      search starts behind them as a programmatic dependent and runs under the transfer.  Bit-exact.
+ *   29 test hook for key 27 (0): 1 = the ingest kernel withholds the arrival flag of the last batch element, so the
+ *      search's CTAs for it give up after their patience, the step is redone on the direct path (results stay
+ *      correct) and ga_debug_host_streamed() reports -1.
  *   28 ga_knn_dists on knn_slab_kernel (1): 0 = never, 1 = batches of at least half a wave of 512-query CTAs, 2 = always
  *      (clouds of 512..2048 points, k <= 10).  Values are the same bits as knn_kernel's.
  * Clouds far from the origin (relative to their size): the filters' windows scale with (max|q_c| + max|t_c|)^2 measured

@@ -361,6 +361,45 @@ def _streamed_ingest_case(ga, key, groups, mirror):
         lib.ga_set_tuning(0, 0)
 
 
+def test_fwd_bwd_host_pulled_ingest_gives_up_and_redoes_the_step(ga):
+    """The safety net of the pulled pipeline: if an arrival flag never comes (test hook, key 29: the ingest kernel
+    withholds the last one), the search's CTAs for that batch element leave after their patience, the host entry sees
+    the give-up word, drops the graph, redoes THAT step on the direct path -- the caller gets correct results -- and
+    keeps the buffer set off the pulled pipeline from then on."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    lib.ga_debug_host_streamed.restype = ctypes.c_int
+    p = ctypes.c_void_p
+    b, n, m = 50, 2048, 2048
+    buf = [torch.empty(b, n, 3).pin_memory(), torch.empty(b, m, 3).pin_memory(), torch.empty(b, n).pin_memory(),
+           torch.empty(b, m).pin_memory(), torch.empty(b, n).pin_memory(),
+           torch.empty(b, n, dtype=torch.int32).pin_memory(), torch.empty(b, m).pin_memory(),
+           torch.empty(b, m, dtype=torch.int32).pin_memory(), torch.empty(b, n, 3).pin_memory(),
+           torch.empty(b, m, 3).pin_memory()]
+    lib.ga_set_tuning(29, 1)
+    try:
+        states = []
+        for it in range(4):
+            seed = 900 + 3 * it
+            a, c = cloud(seed, (b, n, 3)), cloud(seed + 1, (b, m, 3))
+            gd1 = np.random.default_rng(seed).standard_normal((b, n)).astype(np.float32)
+            gd2 = np.random.default_rng(seed + 1).standard_normal((b, m)).astype(np.float32)
+            for dst, src in zip(buf[:4], (a, c, gd1, gd2)):
+                dst.copy_(torch.from_numpy(src))
+            for o in buf[4:]:
+                o.zero_()
+            _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, *[p(x.data_ptr()) for x in buf], 0))
+            states.append(lib.ga_debug_host_streamed())
+            dev = ga.nn_distance(t(a), t(c))
+            g = ga.nn_distance_grad(t(a), t(c), t(gd1), dev[1], t(gd2), dev[3])
+            for x, y in zip(buf[4:], tuple(dev) + tuple(g)):
+                assert bits_equal(x.numpy(), y.cpu().numpy()), (it, states)
+        # call 0 direct, call 1 captures the pulled pipeline and gives up (-1), later calls: chunked pipeline (0)
+        assert states[0] == 0 and states[1] == -1 and all(v == 0 for v in states[2:]), states
+    finally:
+        lib.ga_set_tuning(29, 0)
+
+
 def test_fwd_bwd_host_streamed_ingest_not_for_ragged_lines(ga):
     """Clouds that are not whole 128-byte lines (m = 2000) and launches that do not take the HMMA grid kernel
     (B = 10: tcgen05 kernel) stay on the chunked pipeline."""
