@@ -306,3 +306,43 @@ def test_knn_slab_full_size_config5(ga, oracle):
     assert torch.equal(got, want)
     sel = np.arange(0, 500, 16)
     assert bits_equal(got[sel].cpu().numpy(), oracle.knn_dists(pc[sel], 10))
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_knn_slab_randomised_against_full_scan(ga, seed):
+    """Random cloud sizes, k, anisotropic scales, offsets, cluster mixtures, repeated x values and coincident points:
+    knn_slab_kernel == knn_kernel bit for bit (the window bound, the bin mapping and the overflow service all have to
+    hold for any geometry)."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1000 + seed)
+    b = int(rng.integers(1, 5))
+    n = int(rng.integers(512, 2049))
+    k = int(rng.integers(1, 11))
+    kind = seed % 6
+    pc = rng.random((b, n, 3), dtype=np.float32) - np.float32(0.5)
+    if kind == 1:    # anisotropic box, far from the origin
+        pc = pc * np.array([10.0 ** rng.uniform(-3, 3), 10.0 ** rng.uniform(-3, 3), 10.0 ** rng.uniform(-3, 3)], np.float32)
+        pc = pc + np.float32(10.0 ** rng.uniform(-2, 2))
+    elif kind == 2:  # mixture of tight clusters of very different sizes
+        c = rng.integers(0, 5, (b, n, 1))
+        pc = (rng.standard_normal((b, n, 3)) * (10.0 ** (-1.0 - c))).astype(np.float32) + (c * 0.37).astype(np.float32)
+    elif kind == 3:  # x quantised to a few hundred values (full bins), y / z free
+        pc[..., 0] = np.round(pc[..., 0] * 150.0) / 150.0
+    elif kind == 4:  # a quarter of the points coincide with other points
+        idx = rng.integers(0, n, (b, n // 4))
+        for bi in range(b):
+            pc[bi, : n // 4] = pc[bi, idx[bi]]
+    elif kind == 5:  # a surface: points on a paraboloid sheet plus a few outliers far away
+        pc[..., 2] = pc[..., 0] ** 2 + pc[..., 1] ** 2
+        pc[:, :3] += np.float32(40.0)
+    pc = np.ascontiguousarray(pc.astype(np.float32))
+    lib.ga_set_tuning(28, 2)
+    try:
+        got = ga.knn_dists(t(pc), k)
+        assert lib.ga_last_kernel().decode() == "knn_slab_kernel"
+        lib.ga_set_tuning(28, 0)
+        want = ga.knn_dists(t(pc), k)
+    finally:
+        lib.ga_set_tuning(28, 1)
+    assert bits_equal(got.cpu().numpy(), want.cpu().numpy()), (seed, kind, b, n, k, int((got != want).sum()))
