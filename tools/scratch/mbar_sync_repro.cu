@@ -18,7 +18,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 }
 __global__ void __launch_bounds__(768) repro(int steps, int* out) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 1024);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 217472);  // the offset the barriers have in nn_fwd_umma_kernel
   const uint32_t bar0 = s32(bars);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(768) repro(int steps, int* out) {
 int main() {
   int* out;
   cudaMalloc(&out, 64 * sizeof(int));
-  cudaFuncSetAttribute(repro, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  repro<<<8, 768, 200 * 1024>>>(8, out);
+  cudaFuncSetAttribute(repro, cudaFuncAttributeMaxDynamicSharedMemorySize, 217584);
+  repro<<<8, 768, 217584>>>(8, out);
   cudaError_t e = cudaDeviceSynchronize();
   printf("repro: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
