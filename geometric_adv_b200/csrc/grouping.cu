@@ -1045,7 +1045,31 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
 #define SLAB_CLK(i)
 #endif
 
-  // ---- the cloud: coordinates to registers, x range, max |coordinate|, finiteness ----
+  // ---- the cloud: one bulk copy (TMA, cp.async.bulk global -> shared, completion on an mbarrier) into the queue
+  // region, which is not needed before the second scan; clouds that are not whole 16-byte units fall back to loads
+  __shared__ __align__(8) unsigned long long raw_bar;
+  const float* raw = reinterpret_cast<const float*>(queue);
+  const unsigned raw_bytes = (unsigned)n * 12u;
+  const bool bulk = (raw_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;  // uniform over the CTA
+  if (bulk) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&raw_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(raw_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(queue)),
+                   "l"(pts), "r"(raw_bytes), "r"(bar)
+                   : "memory");
+    }
+    __syncthreads();  // the barrier is initialised for everybody
+    unsigned done = 0;
+    for (int spin = 0; spin < (1 << 24) && !done; spin++)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(bar) : "memory");
+    if (!done) __trap();  // a copy that never lands: fail loudly instead of hanging
+  }
+  // ---- coordinates to registers, x range, max |coordinate|, finiteness ----
   float px[PPT], py[PPT], pz[PPT];
   float xmin = kInf, xmax = -kInf, amax = 0.0f;
   bool bad = false;
@@ -1053,9 +1077,15 @@ __global__ void __launch_bounds__(256, 2) knn_slab_kernel(const KnnArgs a) {
   for (int e = 0; e < PPT; e++) {
     const int i = tid + e * THREADS;
     const bool in = i < n;
-    px[e] = in ? __ldg(pts + (size_t)i * 3) : 0.0f;
-    py[e] = in ? __ldg(pts + (size_t)i * 3 + 1) : 0.0f;
-    pz[e] = in ? __ldg(pts + (size_t)i * 3 + 2) : 0.0f;
+    if (bulk) {
+      px[e] = in ? raw[3 * i] : 0.0f;
+      py[e] = in ? raw[3 * i + 1] : 0.0f;
+      pz[e] = in ? raw[3 * i + 2] : 0.0f;
+    } else {
+      px[e] = in ? __ldg(pts + (size_t)i * 3) : 0.0f;
+      py[e] = in ? __ldg(pts + (size_t)i * 3 + 1) : 0.0f;
+      pz[e] = in ? __ldg(pts + (size_t)i * 3 + 2) : 0.0f;
+    }
     if (in) {
       xmin = fminf(xmin, px[e]);
       xmax = fmaxf(xmax, px[e]);
