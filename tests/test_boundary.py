@@ -122,3 +122,16 @@ def test_ops_are_registered_with_torch_library():
         assert val.shape == (3, 200, 5) and idx.dtype == torch.int32
         assert ns.knn_dists(a, 10).shape == (3, 100, 10)
         assert ns.group_point(a, idx).shape == (3, 200, 5, 3)
+
+
+def test_every_tuning_key_is_documented_in_the_header():
+    """ga_set_tuning's keys (core.cu) and the table in include/ga_b200.h must not drift apart."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    core = open(os.path.join(root, "geometric_adv_b200", "csrc", "core.cu")).read()
+    hdr = open(os.path.join(root, "include", "ga_b200.h")).read()
+    keys = sorted(set(int(k) for k in re.findall(r"key == (\d+)", core)))
+    assert keys and keys[0] == 0
+    table = hdr[hdr.index("Tuning hooks for benchmarks and tests"):hdr.index("int ga_set_tuning(int key, int value);")]
+    missing = [k for k in keys if not re.search(r"(^|[\s*(])%d\s+[a-zA-Z]" % k, table)]
+    assert not missing, "tuning keys without an entry in the header's table: %s" % missing
