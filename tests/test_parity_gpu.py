@@ -361,6 +361,35 @@ def _streamed_ingest_case(ga, key, groups, mirror):
         lib.ga_set_tuning(0, 0)
 
 
+@pytest.mark.parametrize("shape", [(600, 2048, 2048), (1500, 1024, 1024), (700, 2048, 512)])
+def test_fwd_bwd_host_pulled_ingest_large_batches(ga, shape):
+    """Default dispatch at batch sizes where the search runs many waves behind the ingest (a waiting CTA's patience
+    scales with the transfer): the replay is the pulled pipeline and the results are the device entry points' bits."""
+    from geometric_adv_b200 import _lib
+    lib = _lib.load()
+    lib.ga_debug_host_streamed.restype = ctypes.c_int
+    p = ctypes.c_void_p
+    b, n, m = shape
+    g = torch.Generator().manual_seed(b)
+    buf = [(torch.rand(b, n, 3, generator=g) - 0.5).pin_memory(), (torch.rand(b, m, 3, generator=g) - 0.5).pin_memory(),
+           torch.randn(b, n, generator=g).pin_memory(), torch.randn(b, m, generator=g).pin_memory(),
+           torch.empty(b, n).pin_memory(), torch.empty(b, n, dtype=torch.int32).pin_memory(),
+           torch.empty(b, m).pin_memory(), torch.empty(b, m, dtype=torch.int32).pin_memory(),
+           torch.empty(b, n, 3).pin_memory(), torch.empty(b, m, 3).pin_memory()]
+    states = []
+    for it in range(3):
+        for o in buf[4:]:
+            o.fill_(-3)
+        _lib.check(lib.ga_nn_distance_fwd_bwd_host(b, n, m, *[p(x.data_ptr()) for x in buf], 0))
+        states.append(lib.ga_debug_host_streamed())
+    assert states == [0, 1, 1], states
+    a, c = buf[0].cuda(), buf[1].cuda()
+    dev = ga.nn_distance(a, c)
+    gr = ga.nn_distance_grad(a, c, buf[2].cuda(), dev[1], buf[3].cuda(), dev[3])
+    for x, y in zip(buf[4:], tuple(dev) + tuple(gr)):
+        assert torch.equal(x, y.cpu()), shape
+
+
 def test_fwd_bwd_host_pulled_ingest_gives_up_and_redoes_the_step(ga):
     """The safety net of the pulled pipeline: if an arrival flag never comes (test hook, key 29: the ingest kernel
     withholds the last one), the search's CTAs for that batch element leave after their patience, the host entry sees
