@@ -897,9 +897,12 @@ __global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
 // ga_knn_dists returns VALUES only (sqrt of the k+1 smallest squared distances of every point to its own cloud, the
 // first dropped: get_knn_dists_per_point.py:78-81), so neither the order of equal distances nor the identity of the
 // neighbours matters, and the cloud may be reordered.  Per CTA (= cloud, 512 queries) the cloud is counting-sorted
-// by x into 1024 bins (every CTA of a cloud sorts it again: ~2 us against ~15 us of search) and staged in that order;
+// by x into 1024 bins (every CTA of a cloud sorts it again: ~7 % of a CTA), the points of a bin ordered by index so
+// that the CTAs of a cloud agree on the sorted positions they split the queries by, and staged in that order (the raw
+// cloud arrives by one TMA bulk copy);
 // a warp owns 64 queries that are neighbours in the sorted order, i.e. a thin slab [xa, xb] of the cloud.
-//   A0  filter scan (nn_tiles.cuh) over the warp's own positions +- kSlabSeed targets: the K-th smallest minimum
+//   A0  filter scan (nn_tiles.cuh) over the warp's own positions +- kSlabSeed targets (the same count at the ends of
+//       the cloud, where one side is cut off and a half ball reaches further): the K-th smallest minimum
 //       over tiles of 16 targets is tau, K distinct targets with filter value <= tau.  Hence the K-th smallest
 //       exact distance of query j is at most U_j = tau_j + |q_j|^2 + error terms.
 //   r   r^2 >= max_j U_j over the warp.  A target whose x lies outside [xa - r, xb + r] (directed rounding) has
@@ -908,7 +911,8 @@ __global__ void __launch_bounds__(Cfg::kThreads) knn_kernel(const KnnArgs a) {
 //       the window are a contiguous range of the sorted order, found from the bin starts.
 //   B1  second scan over that range only: targets with f <= tau + W (the window of knn_kernel) go to the query's queue;
 //   B2  queued targets in the reference arithmetic into an exact sorted list of K values, written as sqrt.
-// On uniform clouds of 2048 points A0 sees ~19 % and B1 ~35 % of the cloud where knn_kernel scans all of it twice.
+// On uniform clouds of 2048 points A0 sees 25 % and B1 ~34 % of the cloud where knn_kernel scans all of it twice
+// (config 5: 0.48 ms against 0.97; DESIGN.md 4.3 has the measurements and the two profiler findings on the way).
 // A query whose queue overflows (dense clusters) is served by the whole warp with K selection passes over the
 // cloud.  A cloud with a non-finite or huge coordinate, or fewer than 512 points, is handed to knn_body unchanged
 // (NaN distances take part in the reference's selection sort in a way only its replay reproduces).
