@@ -363,11 +363,14 @@ __device__ __forceinline__ void filter_collect(const float4* __restrict__ tgt, i
                                                int jstride, int cap) {
   constexpr int U = kPipeU;
   constexpr int NB = (T / 2) / U;
-  unsigned short* qp[Q];
+  // running append positions as 32-bit shared-memory addresses: a generic pointer costs a 64-bit add per append
+  uint32_t qp[Q], qb[Q];
   bool over[Q];
+  const uint32_t rowb = 2u * (uint32_t)qstride;  // bytes from one queue row to the next
 #pragma unroll
   for (int j = 0; j < Q; j++) {
-    qp[j] = queue + j * jstride;
+    qb[j] = (uint32_t)__cvta_generic_to_shared(queue + j * jstride);
+    qp[j] = qb[j];
     over[j] = false;
   }
   float4 buf[2][2 * U];
@@ -389,27 +392,27 @@ __device__ __forceinline__ void filter_collect(const float4* __restrict__ tgt, i
         for (int j = 0; j < Q; j++) {
           const float2 f = filter_pair(u, v, ax2[j], ay2[j], az2[j]);
           if (!(f.x > thr[j])) {  // NaN filter value / threshold counts as a candidate
-            *qp[j] = (unsigned short)(gb + (blk * U + pp) * 2);
-            qp[j] += qstride;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(qp[j]), "h"((unsigned short)(gb + (blk * U + pp) * 2)) : "memory");
+            qp[j] += rowb;
           }
           if (!(f.y > thr[j])) {
-            *qp[j] = (unsigned short)(gb + (blk * U + pp) * 2 + 1);
-            qp[j] += qstride;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(qp[j]), "h"((unsigned short)(gb + (blk * U + pp) * 2 + 1)) : "memory");
+            qp[j] += rowb;
           }
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < Q; j++) {
-      if ((int)(qp[j] - (queue + j * jstride)) > cap * qstride) {  // too many: stop collecting
+      if (qp[j] - qb[j] > (uint32_t)cap * rowb) {  // too many: stop collecting
         over[j] = true;
-        qp[j] = queue + j * jstride;
+        qp[j] = qb[j];
         thr[j] = -__int_as_float(0x7f800000);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < Q; j++) cnt[j] = over[j] ? cap + 1 : (int)(qp[j] - (queue + j * jstride)) / qstride;
+  for (int j = 0; j < Q; j++) cnt[j] = over[j] ? cap + 1 : (int)((qp[j] - qb[j]) / rowb);
 }
 
 // Window of the filter (see nn_distance_fwd.cu): W = 128u (A+Bm)^2 + denormal slack.
