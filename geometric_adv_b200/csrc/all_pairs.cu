@@ -135,7 +135,7 @@ __device__ __noinline__ void pair_job(const float* __restrict__ qpts, const floa
   float mrun[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) mrun[r] = kMmaBig;
-  mma_chunk<MODE>(R, s, mrun, tgt, bfrag, 0, n, n, bm, wcnt, wtile, lane);
+  mma_chunk<MODE, true>(R, s, mrun, tgt, bfrag, 0, n, n, bm, wcnt, wtile, lane);  // batched accumulators: see mma_scan_range
 #pragma unroll
   for (int j = 0; j < 2; j++) {
     if (!s.valid[j]) continue;

@@ -202,7 +202,11 @@ __device__ __forceinline__ int mma_key_tile(float key, int t) { return ((__float
 // block number (the tile is 4 blk + t, t known from the lane); KEYBITS = 6: it carries the whole tile
 // number 4 blk + t, so that keys of different lanes can be merged (quad_merge; 64 ulp <= 384u s^2 of
 // perturbation: callers use mma_window_wide).
-template <int KEYBITS>
+// BATCH: the four MMAs of a B fragment are issued into four accumulator quads of their own before any of them is
+// folded.  In a kernel whose job loop keeps many values live (all_pairs.cu) ptxas otherwise puts every HMMA of the
+// scan on ONE quad with a NOP behind it (1.04 G NOPs for 1.07 G HMMAs, 32 % of the samples: ncu of
+// all_pairs_directed_mma_kernel, round 2) -- whether the scan is inlined or sits behind a call.
+template <int KEYBITS, bool BATCH = false>
 __device__ __forceinline__ void mma_scan_range(const MmaRows& R, const uint2* __restrict__ bfrag, int blk0, int blk1,
                                                int lane, MmaTrack& tr) {
   static_assert(KEYBITS == 4 || KEYBITS == 6, "key layouts");
@@ -217,12 +221,23 @@ __device__ __forceinline__ void mma_scan_range(const MmaRows& R, const uint2* __
 #pragma unroll
     for (int j = 0; j < 16; j++) {
       const uint2 bf = bp[j * 32];
+      if constexpr (BATCH) {
+        float c[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float c[4];
-        mma16816(c, R.a[i], bf.x, bf.y);
-        rm[2 * i] = fmin3(rm[2 * i], c[0], c[1]);
-        rm[2 * i + 1] = fmin3(rm[2 * i + 1], c[2], c[3]);
+        for (int i = 0; i < 4; i++) mma16816(c[i], R.a[i], bf.x, bf.y);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          rm[2 * i] = fmin3(rm[2 * i], c[i][0], c[i][1]);
+          rm[2 * i + 1] = fmin3(rm[2 * i + 1], c[i][2], c[i][3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          float c[4];
+          mma16816(c, R.a[i], bf.x, bf.y);
+          rm[2 * i] = fmin3(rm[2 * i], c[0], c[1]);
+          rm[2 * i + 1] = fmin3(rm[2 * i + 1], c[2], c[3]);
+        }
       }
     }
     const int id = KEYBITS == 4 ? blk : 4 * blk + (lane & 3);
@@ -453,7 +468,7 @@ __device__ __forceinline__ void mma_init_queries(QueryState<2>& s, const float* 
 // One staged chunk (targets [c0, c0 + cn) of a cloud with nt points) for one warp: tensor-core
 // scan, per-query lists of the qualifying tiles, exact refine.  mrun: running row minima of h over
 // the chunks seen so far (same value in the 4 lanes of a quad); wcnt / wtile: this warp's lists.
-template <int MODE>
+template <int MODE, bool SCAN_BATCH = false>
 __device__ __forceinline__ void mma_chunk(const MmaRows& R, QueryState<2>& s, float (&mrun)[8],
                                           const float4* __restrict__ tgt, const uint4* __restrict__ bfrag, int c0, int nt,
                                           int cn, float bm_run, int* __restrict__ wcnt,
@@ -468,7 +483,10 @@ __device__ __forceinline__ void mma_chunk(const MmaRows& R, QueryState<2>& s, fl
   __syncwarp();
 
   MmaTrack tr;
-  mma_scan(R, reinterpret_cast<const uint2*>(bfrag), nblk, lane, tr);
+  if constexpr (SCAN_BATCH)
+    mma_scan_range<4, true>(R, reinterpret_cast<const uint2*>(bfrag), 0, nblk, lane, tr);
+  else
+    mma_scan(R, reinterpret_cast<const uint2*>(bfrag), nblk, lane, tr);
 
   // Row minimum over the quad, window, and the qualifying tiles of this lane -> per-query lists.
   float mythr[2] = {0.0f, 0.0f};
