@@ -545,9 +545,11 @@ def leg_knn(dev, world, rank, fp32_peak, flush, quick):
         full = sharding.all_gather_rows(part, b)
         ev[r][2].record()
     torch.cuda.synchronize()
-    t_k = sum(e[0].elapsed_time(e[1]) for e in ev) / reps
-    t_g = sum(e[1].elapsed_time(e[2]) for e in ev) / reps
-    t_all = sum(e[0].elapsed_time(e[2]) for e in ev) / reps
+    # median over the repetitions: one descheduled repetition (seen once: 10 ms in a 0.5 ms leg) must not set the figure
+    med = lambda xs: sorted(xs)[len(xs) // 2]
+    t_k = med([e[0].elapsed_time(e[1]) for e in ev])
+    t_g = med([e[1].elapsed_time(e[2]) for e in ev])
+    t_all = med([e[0].elapsed_time(e[2]) for e in ev])
     t_k, t_g, t_all = _max_over_ranks([t_k, t_g, t_all], dev, world)
     from geometric_adv_b200 import _lib
     knn_kernel_name = _lib.load().ga_last_kernel().decode()  # knn_slab_kernel for large shards, knn_kernel below
