@@ -545,8 +545,8 @@ def leg_knn(dev, world, rank, fp32_peak, flush, quick):
         full = sharding.all_gather_rows(part, b)
         ev[r][2].record()
     torch.cuda.synchronize()
-    # median over the repetitions (one run's MEAN came out at three times the usual figure; a rerun on another box
-    # gave the usual one: profiles/bench_r02_rerun.json): a single slow repetition must not set the figure
+    # median over the repetitions (one run's MEAN came out at three times the usual figure, reruns at the usual one):
+    # a single slow repetition must not set the figure
     med = lambda xs: sorted(xs)[len(xs) // 2]
     t_k = med([e[0].elapsed_time(e[1]) for e in ev])
     t_g = med([e[1].elapsed_time(e[2]) for e in ev])
